@@ -1,0 +1,228 @@
+/*
+ * ptg_b200.h -- C ABI of the B200-native batched PtG environment (libptg_b200.so).
+ *
+ * Drop-in boundary for the PTGEnv.step()/reset() hot path of SimMarkt/RL_PtG.  The reference has no FFI of
+ * its own (it is pure Python); every entry point below names the reference interface it replaces
+ * (file:line relative to the reference checkout).  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *   - return value 0 = PTG_OK, negative = PtgStatus error; ptg_last_error() gives the message (thread-local).
+ *     The reference signals these conditions with Python `assert` (env/ptg_gym_env.py:46,158,204,357,440).
+ *   - "host" pointers are read during the call only.  "device" pointers are caller-owned CUDA memory
+ *     (e.g. torch tensors' data_ptr()); the library never frees them and keeps none past the call.
+ *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*); no call synchronises the
+ *     device except ptg_create / ptg_destroy / ptg_get_state / ptg_set_state / ptg_poll_error.
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef PTG_B200_H_
+#define PTG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTG_ABI_VERSION 1
+#define PTG_N_DATASETS 17
+#define PTG_N_INFO 24        /* fields of PTGEnv._get_info(), env/ptg_gym_env.py:251-278 */
+#define PTG_MAX_PRICE_AHEAD 16
+
+/* Methanation time-series tables, in the order of the reference's op_data_files (src/rl_utils.py:104-110). */
+enum PtgDataset {
+    PTG_DS_STARTUP_COLD = 0, PTG_DS_STARTUP_HOT = 1, PTG_DS_COOLDOWN = 2, PTG_DS_STANDBY_DOWN = 3,
+    PTG_DS_STANDBY_UP = 4, PTG_DS_OP1_START_P = 5, PTG_DS_OP2_START_F = 6, PTG_DS_OP3_P_F = 7,
+    PTG_DS_OP4_P_F_P_5 = 8, PTG_DS_OP5_P_F_P_10 = 9, PTG_DS_OP6_P_F_P_15 = 10, PTG_DS_OP7_P_F_P_22 = 11,
+    PTG_DS_OP8_F_P = 12, PTG_DS_OP9_F_P_F_5 = 13, PTG_DS_OP10_F_P_F_10 = 14, PTG_DS_OP11_F_P_F_15 = 15,
+    PTG_DS_OP12_F_P_F_20 = 16
+};
+
+/* Plant states == action ids (config_env.yaml:73-78; env/ptg_gym_env.py:50-56,142). */
+enum PtgPlantState { PTG_STANDBY = 0, PTG_COOLDOWN = 1, PTG_STARTUP = 2, PTG_PARTIAL_LOAD = 3, PTG_FULL_LOAD = 4 };
+
+typedef enum PtgStatus {
+    PTG_OK = 0,
+    PTG_ERR_INVALID_ARGUMENT = -1,   /* bad config value (reference: assert at ptg_gym_env.py:46,158,204) */
+    PTG_ERR_CUDA = -2,               /* CUDA runtime error */
+    PTG_ERR_UNSUPPORTED = -3,        /* valid in the reference but outside this build's limits */
+    PTG_ERR_INVALID_ACTION = -4,     /* device saw an action outside 0..4 (reference: ptg_gym_env.py:347,440) */
+    PTG_ERR_DATA_RANGE = -5,         /* device indexed past the market tables (reference: IndexError) */
+    PTG_ERR_NOISE_TAPE = -6,         /* tape-mode noise ran past the end of the tape */
+    PTG_ERR_NCCL = -7
+} PtgStatus;
+
+enum PtgActionDtype { PTG_ACT_I64 = 0, PTG_ACT_I32 = 1, PTG_ACT_U8 = 2, PTG_ACT_F32 = 3 };
+
+/* Source of the Gaussian row jitter drawn on transitions into standby/cooldown/startup
+ * (np_random.normal(0, noise, size=1)[0]; env/ptg_gym_env.py:584-585,598-599,620-621). */
+enum PtgNoiseMode {
+    PTG_NOISE_NUMPY = 0,   /* on-device PCG64 + ziggurat: bit-identical to numpy's Generator(PCG64(seed)).normal */
+    PTG_NOISE_TAPE = 1,    /* caller-supplied pre-drawn fp64 tape, consumed in order (parity harness) */
+    PTG_NOISE_OFF = 2      /* noise term is exactly 0.0 (no draw) */
+};
+
+/* Episode schedule: which eps_ind entry env e uses for its m-th constructor/reset (m = 0 is the constructor).
+ * Reference: module-global ep_index, env/ptg_gym_env.py:9,37-44,59-62,487-493. */
+enum PtgScheduleMode {
+    PTG_SCHED_DUMMY = 0,   /* DummyVecEnv order: eps_ind[(n_envs_global*m + global_env_id) mod len] */
+    PTG_SCHED_SUBPROC = 1  /* SubprocVecEnv: per-env start offset in [0, n_eps_loops), then +1 per reset */
+};
+
+/* All scalar knobs the env reads from its constructor dict (src/rl_utils.py:345-403). */
+typedef struct PtgConfig {
+    int32_t abi_version;            /* = PTG_ABI_VERSION */
+    int32_t scenario;               /* 1, 2, 3 -> b_s3 = (scenario == 3), ptg_gym_env.py:76-77 */
+    int32_t raw_modified;           /* 0 = "raw", 1 = "mod" */
+    int32_t action_type;            /* 0 = "discrete", 1 = "continuous" */
+    int32_t train_or_eval;          /* 0 = "train" (step info empty), 1 = "eval" (24-field info every step) */
+    int32_t price_ahead;
+    int32_t sim_step;               /* [s] */
+    int32_t time_step_op;           /* [s] */
+    int32_t eps_sim_steps;
+    int32_t noise_mode;             /* PtgNoiseMode */
+    int32_t schedule_mode;          /* PtgScheduleMode */
+    int32_t n_eps_loops;
+    /* load-change thresholds [rows], config_env.yaml:133-155 */
+    int32_t time1_start_p_f, time2_start_f_p, time_p_f, time_f_p;
+    int32_t time1_p_f_p, time2_p_f_p, time23_p_f_p, time3_p_f_p, time34_p_f_p, time4_p_f_p, time45_p_f_p,
+            time5_p_f_p;
+    int32_t time1_f_p_f, time2_f_p_f, time23_f_p_f, time3_f_p_f, time34_f_p_f, time4_f_p_f, time45_f_p_f,
+            time5_f_p_f;
+    int32_t i_fully_developed, j_fully_developed;
+    int32_t _pad0;
+    double noise;                   /* sigma [rows] */
+    double eps_len_d;               /* [d] */
+    double state_change_penalty;
+    double reward_level;            /* r_0 = reward_level[0] */
+    double convert_mol_to_Nm3, H_u_CH4, H_u_H2, dt_water, cp_water, rho_water, Molar_mass_CO2, Molar_mass_H2O,
+           h_H2O_evap, eeg_el_price, heat_price, o2_price, water_price, min_load_electrolyzer,
+           max_h2_volumeflow, eta_CHP;
+    double t_cat_standby, t_cat_startup_cold, t_cat_startup_hot;
+    double el_l_b, el_u_b, gas_l_b, gas_u_b, eua_l_b, eua_u_b, T_l_b, T_u_b, h2_l_b, h2_u_b, ch4_l_b, ch4_u_b,
+           h2_res_l_b, h2_res_u_b, h2o_l_b, h2o_u_b, heat_l_b, heat_u_b, rew_l_b, rew_u_b;
+} PtgConfig;
+
+/* Host arrays of the constructor dict (read during ptg_create only). */
+typedef struct PtgTables {
+    const double* op[PTG_N_DATASETS];     /* row-major [op_rows[d]][7]: t, T_cat, n_h2, n_ch4, n_h2_res, m_h2o, P_el */
+    int64_t op_rows[PTG_N_DATASETS];
+    const double* e_r_b;                  /* [3][price_ahead][n_hours]  el_price, pot_rew, part_full */
+    int64_t n_hours;
+    const double* g_e;                    /* [2][2][n_days]  gas, eua x (today, tomorrow) */
+    int64_t n_days;
+    const int64_t* eps_ind;               /* training episode order, or NULL for val/test envs */
+    int64_t n_eps_ind;
+} PtgTables;
+
+/* Device output/input buffers of one step()/reset() call.  obs is ONE fp32 buffer of obs_dim*n_envs elements,
+ * key-major (each observation key is a contiguous [n_envs, key_dim] block, keys in the order of
+ * env/ptg_gym_env.py:222-249); METH_STATUS holds int32 bit patterns.  See ptg_obs_layout(). */
+typedef struct PtgIO {
+    float* obs;              /* [obs_dim * n_envs] */
+    float* reward;           /* [n_envs]; NULL allowed for ptg_reset */
+    uint8_t* done;           /* [n_envs]; NULL allowed for ptg_reset */
+    float* terminal_obs;     /* same layout as obs, written only for envs with done=1 (SB3 "terminal_observation");
+                                NULL = do not record */
+    double* info;            /* [PTG_N_INFO][n_envs] feature-major fp64, or NULL.  Written by ptg_reset always
+                                (reference reset() returns the full info even in train mode, :503-506) and by
+                                ptg_step when train_or_eval = eval.  For done envs it holds the terminal step's
+                                info (SB3 keeps the pre-reset info). Meth_Action is the action id 0..4. */
+    double* episode_return;  /* [n_envs] Monitor-style sum of returned rewards of the episode that just ended */
+    int32_t* episode_length; /* [n_envs] its length; both written only where done=1; NULL allowed */
+} PtgIO;
+
+/* One observation key of the obs buffer. */
+typedef struct PtgObsKey {
+    char name[24];
+    int32_t dim;             /* values per env */
+    int32_t is_int32;        /* 1 for METH_STATUS */
+    int64_t offset;          /* element offset of the [n_envs, dim] block inside obs */
+} PtgObsKey;
+
+/* Episode statistics of finished episodes since the last clear (per rank; combine across ranks with
+ * ptg_stats_combine or any all-gather of this 64-byte struct). */
+typedef struct PtgEpisodeStats {
+    double count, sum_return, sum_return_sq, sum_length, min_return, max_return;
+    double total_steps;      /* env-steps executed since the last clear */
+    double _reserved;
+} PtgEpisodeStats;
+
+typedef struct PtgHandle PtgHandle;
+
+/* PTGEnv.__init__ for n_envs environments (env/ptg_gym_env.py:28-79) + DummyVecEnv/make_vec_env construction
+ * (src/rl_utils.py:448-453).  Uploads the tables, builds the device look-up tables with CUDA kernels and
+ * constructs the envs (each consumes one eps_ind entry like the reference constructor, :59-62).
+ * env_id_offset / n_envs_global describe this shard of a larger env population (multi-GPU): global env id =
+ * env_id_offset + local index; schedules and seeds depend on the global id only. */
+int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t n_envs, int64_t env_id_offset,
+               int64_t n_envs_global, int device, PtgHandle** out);
+
+void ptg_destroy(PtgHandle* h);
+
+/* VecEnv.seed(seed) + VecEnv.reset() (SB3) over PTGEnv.reset(seed) (env/ptg_gym_env.py:483-506).
+ *   seeds : host int64[n_envs] or NULL.  Env e with seeds[e] >= 0 re-creates its generator as
+ *           Generator(PCG64(SeedSequence(seeds[e]))) (gymnasium Env.reset(seed=...)); negative = keep stream.
+ *   mask  : host uint8[n_envs] or NULL (= all).  Only masked envs are reset.
+ * Writes obs (and info when io->info != NULL) for the reset envs. */
+int ptg_reset(PtgHandle* h, const int64_t* seeds, const uint8_t* mask, const PtgIO* io, void* stream);
+
+/* VecEnv.step_wait() over PTGEnv.step(action) (env/ptg_gym_env.py:336-481) with SB3 auto-reset:
+ * where done=1 the returned obs is the reset obs, io->terminal_obs gets the last obs.
+ *   actions : device pointer, n_envs elements of `action_dtype` (F32 = continuous Box(-1,1) actions). */
+int ptg_step(PtgHandle* h, const void* actions, int action_dtype, const PtgIO* io, void* stream);
+
+/* T consecutive steps in one launch with the per-env state kept in registers.
+ *   actions : device [T][n_envs];  io buffers are [T] x the single-step shapes (obs: [T][obs_dim*n_envs], ...).
+ * terminal_obs / info / episode_* are not recorded by this entry point (must be NULL). */
+int ptg_step_many(PtgHandle* h, const void* actions, int action_dtype, int32_t T, const PtgIO* io, void* stream);
+
+/* Tape-mode noise: device fp64 [n_envs][tape_len], values as returned by normal(0, noise) (already scaled). */
+int ptg_set_noise_tape(PtgHandle* h, const double* tape_dev, int64_t tape_len);
+
+/* Plant state snapshot (host SoA arrays of n_envs each; any pointer may be NULL).  Used by parity tests and
+ * checkpointing (the reference never checkpoints env state). */
+typedef struct PtgStateSoA {
+    int32_t* meth_state;     /* Meth_State */
+    int32_t* i;              /* row index i */
+    int32_t* j;              /* step counter j */
+    int32_t* k;              /* step in episode */
+    int32_t* hot_cold;
+    int32_t* standby_ds;     /* PtgDataset currently bound to self.standby / startup / partial / full */
+    int32_t* startup_ds;
+    int32_t* partial_ds;
+    int32_t* full_ds;
+    int32_t* current_action;
+    int32_t* act_ep_h;
+    int32_t* act_ep_d;
+    int32_t* episode_count;  /* m: constructor/resets consumed so far */
+    int64_t* draws;          /* noise values consumed so far (tape position) */
+    double* t_cat;           /* Meth_T_cat */
+    double* cum_reward;      /* Monitor-style running return (== cum_rew when state_change_penalty == 0) */
+} PtgStateSoA;
+int ptg_get_state(PtgHandle* h, const PtgStateSoA* out);
+int ptg_set_state(PtgHandle* h, const PtgStateSoA* in);
+
+/* Deterministic two-stage reduction (warp shuffles -> per-block partials -> one block) of the finished-episode
+ * accumulators into *stats_dev (device, 64 bytes); clear != 0 zeroes the accumulators afterwards. */
+int ptg_episode_stats(PtgHandle* h, PtgEpisodeStats* stats_dev, int clear, void* stream);
+
+/* Host-side combine of per-rank stats (sum / min / max), e.g. after an NCCL all-gather of the 64-byte structs. */
+void ptg_stats_combine(const PtgEpisodeStats* per_rank, int n_ranks, PtgEpisodeStats* out);
+
+/* Sticky device-side error word (invalid action, market-table overrun, tape overrun).  Synchronises `stream`.
+ * Returns PTG_OK or the first error seen since the last poll and clears it. */
+int ptg_poll_error(PtgHandle* h, void* stream);
+
+/* Introspection. */
+int ptg_obs_dim(const PtgHandle* h);                               /* fp32 elements per env */
+int ptg_obs_layout(const PtgHandle* h, PtgObsKey* keys, int max_keys);   /* returns number of keys */
+int64_t ptg_num_envs(const PtgHandle* h);
+int64_t ptg_bytes_per_env_step(const PtgHandle* h, int action_dtype);    /* algorithmic HBM bytes, DESIGN.md */
+int ptg_kernel_launches(const PtgHandle* h, int64_t* out);               /* kernels launched by this handle */
+const char* ptg_last_error(void);
+int ptg_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTG_B200_H_ */
