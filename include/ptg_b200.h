@@ -216,6 +216,7 @@ int ptg_poll_error(PtgHandle* h, void* stream);
 /* Introspection. */
 int ptg_obs_dim(const PtgHandle* h);                               /* fp32 elements per env */
 int ptg_obs_layout(const PtgHandle* h, PtgObsKey* keys, int max_keys);   /* returns number of keys */
+int64_t ptg_obs_elems(const PtgHandle* h);                       /* fp32 elements of one obs buffer (padded) */
 int64_t ptg_num_envs(const PtgHandle* h);
 int64_t ptg_bytes_per_env_step(const PtgHandle* h, int action_dtype);    /* algorithmic HBM bytes, DESIGN.md */
 int ptg_kernel_launches(const PtgHandle* h, int64_t* out);               /* kernels launched by this handle */

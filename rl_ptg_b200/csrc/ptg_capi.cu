@@ -1,0 +1,535 @@
+// ptg_capi.cu -- host side of libptg_b200.so: the C ABI declared in include/ptg_b200.h.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ptg_kernels.cuh"
+#include "ptg_ziggurat_tables.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define PTG_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t err__ = (expr);                                                                      \
+        if (err__ != cudaSuccess)                                                                        \
+            return fail(PTG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));           \
+    } while (0)
+
+inline int64_t round_up4(int64_t x) { return (x + 3) & ~(int64_t)3; }
+inline unsigned blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace
+
+struct PtgHandle {
+    int device = 0;
+    PtgConfig cfg{};
+    DevParams P{};
+    BuildParams B{};
+    std::vector<void*> allocs;
+    std::vector<PtgObsKey> keys;
+    double* d_vals = nullptr;
+    int64_t* d_seeds = nullptr;
+    uint8_t* d_mask = nullptr;
+    StatAcc* d_partial = nullptr;
+    uint32_t* d_err = nullptr;
+    int32_t* d_state_i32 = nullptr;   // scratch for get/set state: 13 int32 arrays
+    int64_t* d_state_i64 = nullptr;
+    double* d_state_f64 = nullptr;    // 2 arrays
+    int64_t launches = 0;
+    double total_steps = 0.0;
+
+    template <typename T>
+    cudaError_t alloc(T** p, size_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) { allocs.push_back(q); *p = static_cast<T*>(q); }
+        return e;
+    }
+    template <typename T>
+    cudaError_t upload(const T** p, const T* host, size_t count) {
+        T* q = nullptr;
+        cudaError_t e = alloc(&q, count);
+        if (e != cudaSuccess) return e;
+        *p = q;
+        return cudaMemcpy(q, host, count * sizeof(T), cudaMemcpyHostToDevice);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel dispatch on (NV, MOD)
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+template <int NV, bool MOD>
+void launch_step_t(PtgHandle* h, const void* actions, int adtype, const PtgIO& io, int T, cudaStream_t st) {
+    k_step<NV, MOD><<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, T);
+}
+template <int NV, bool MOD>
+void launch_reset_t(PtgHandle* h, const int64_t* seeds, const uint8_t* mask, const PtgIO& io, cudaStream_t st) {
+    k_reset<NV, MOD><<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, 0, st>>>(h->P, seeds, mask, io);
+}
+
+#define PTG_DISPATCH(fn, ...)                                                     \
+    do {                                                                          \
+        const bool mod__ = !h->P.raw;                                             \
+        switch (h->P.nv) {                                                        \
+            case 1: mod__ ? fn<1, true>(__VA_ARGS__) : fn<1, false>(__VA_ARGS__); break; \
+            case 2: mod__ ? fn<2, true>(__VA_ARGS__) : fn<2, false>(__VA_ARGS__); break; \
+            case 3: mod__ ? fn<3, true>(__VA_ARGS__) : fn<3, false>(__VA_ARGS__); break; \
+            case 4: mod__ ? fn<4, true>(__VA_ARGS__) : fn<4, false>(__VA_ARGS__); break; \
+            default: mod__ ? fn<5, true>(__VA_ARGS__) : fn<5, false>(__VA_ARGS__); break; \
+        }                                                                         \
+    } while (0)
+
+int validate(const PtgConfig* c, const PtgTables* t, int64_t n_envs, int64_t off, int64_t n_global) {
+    if (!c || !t) return fail(PTG_ERR_INVALID_ARGUMENT, "null config/tables");
+    if (c->abi_version != PTG_ABI_VERSION) return fail(PTG_ERR_INVALID_ARGUMENT, "PtgConfig.abi_version mismatch");
+    if (c->scenario < 1 || c->scenario > 3) return fail(PTG_ERR_INVALID_ARGUMENT, "scenario must be one of [1, 2, 3]");
+    if (c->raw_modified != 0 && c->raw_modified != 1) return fail(PTG_ERR_INVALID_ARGUMENT, "raw_modified must be raw(0) or mod(1)");
+    if (c->action_type != 0 && c->action_type != 1) return fail(PTG_ERR_INVALID_ARGUMENT, "action_type must be discrete(0) or continuous(1)");
+    if (c->train_or_eval != 0 && c->train_or_eval != 1) return fail(PTG_ERR_INVALID_ARGUMENT, "train_or_eval must be train(0) or eval(1)");
+    if (c->noise_mode < 0 || c->noise_mode > 2) return fail(PTG_ERR_INVALID_ARGUMENT, "noise_mode out of range");
+    if (c->schedule_mode < 0 || c->schedule_mode > 1) return fail(PTG_ERR_INVALID_ARGUMENT, "schedule_mode out of range");
+    if (c->price_ahead < 1) return fail(PTG_ERR_INVALID_ARGUMENT, "price_ahead must be >= 1");
+    if (c->price_ahead > PTG_MAX_PRICE_AHEAD) return fail(PTG_ERR_UNSUPPORTED, "price_ahead > 16 is not supported by the packed hour row");
+    if (c->sim_step <= 0 || c->time_step_op <= 0 || c->sim_step / c->time_step_op < 1)
+        return fail(PTG_ERR_INVALID_ARGUMENT, "sim_step / time_step_op must give at least one row per step");
+    if (c->eps_sim_steps < 7) return fail(PTG_ERR_INVALID_ARGUMENT, "eps_sim_steps must be >= 7 (episodes end at eps_sim_steps - 6)");
+    if (n_envs < 1 || off < 0 || n_global < off + n_envs) return fail(PTG_ERR_INVALID_ARGUMENT, "bad n_envs / env_id_offset / n_envs_global");
+    const int S = c->sim_step / c->time_step_op;
+    int64_t total = 0;
+    for (int d = 0; d < PTG_N_DATASETS; ++d) {
+        if (!t->op[d] || t->op_rows[d] < 1) return fail(PTG_ERR_INVALID_ARGUMENT, "missing operation table");
+        total += t->op_rows[d] + 1;
+    }
+    if (t->op_rows[PTG_DS_OP1_START_P] < S)
+        return fail(PTG_ERR_UNSUPPORTED, "op1_start_p shorter than one env step (hand-over window would be truncated)");
+    if (total > (int64_t)0x3fffffff) return fail(PTG_ERR_UNSUPPORTED, "operation tables too large");
+    if (!t->e_r_b || t->n_hours < 1 || !t->g_e || t->n_days < 1) return fail(PTG_ERR_INVALID_ARGUMENT, "missing market tables");
+    if (t->eps_ind && t->n_eps_ind < 1) return fail(PTG_ERR_INVALID_ARGUMENT, "empty eps_ind");
+    // largest i + j*S the state machine can form must fit int32
+    const int64_t max_pos = 200000 + ((int64_t)c->eps_sim_steps + c->j_fully_developed + 2) * S + c->i_fully_developed;
+    if (max_pos > 0x7fffffffLL) return fail(PTG_ERR_UNSUPPORTED, "i + j*step_size would overflow int32");
+    return PTG_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t n_envs, int64_t env_id_offset,
+                          int64_t n_envs_global, int device, PtgHandle** out) {
+    if (!out) return fail(PTG_ERR_INVALID_ARGUMENT, "null out pointer");
+    *out = nullptr;
+    int rc = validate(cfg, tables, n_envs, env_id_offset, n_envs_global);
+    if (rc != PTG_OK) return rc;
+    int ndev = 0;
+    PTG_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PTG_ERR_INVALID_ARGUMENT, "no such CUDA device");
+    PTG_CUDA(cudaSetDevice(device));
+
+    PtgHandle* h = new PtgHandle();
+    h->device = device;
+    h->cfg = *cfg;
+    DevParams& P = h->P;
+    BuildParams& B = h->B;
+    const PtgConfig& c = *cfg;
+#define PTG_TRY(expr)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t err__ = (expr);                                                                      \
+        if (err__ != cudaSuccess) {                                                                      \
+            std::string m__ = std::string(#expr) + ": " + cudaGetErrorString(err__);                     \
+            ptg_destroy(h);                                                                              \
+            return fail(PTG_ERR_CUDA, m__);                                                              \
+        }                                                                                                \
+    } while (0)
+
+    P.n_envs = n_envs; P.env_id_offset = env_id_offset; P.n_envs_global = n_envs_global;
+    P.S = c.sim_step / c.time_step_op;                              // :66
+    P.pa = c.price_ahead;
+    P.nv = (c.price_ahead + 3 + 3) / 4;
+    P.raw = c.raw_modified == 0;
+    P.obs_dim = P.raw ? c.price_ahead + 4 + 9 : 2 * c.price_ahead + 9;
+    P.eps_sim_steps = c.eps_sim_steps; P.sim_step = c.sim_step;
+    P.n_hours = (int32_t)tables->n_hours; P.n_days = (int32_t)tables->n_days;
+    P.n_eps_ind = (int32_t)tables->n_eps_ind;
+    P.continuous = c.action_type; P.eval_mode = c.train_or_eval; P.noise_mode = c.noise_mode;
+    P.schedule_mode = c.schedule_mode; P.b_s3 = c.scenario == 3 ? 1 : 0;     // :76-77
+    P.penalty = c.reward_level * c.state_change_penalty;                       // :332
+    P.has_penalty = P.penalty != 0.0;
+    P.time1_start_p_f = c.time1_start_p_f; P.time2_start_f_p = c.time2_start_f_p; P.time_p_f = c.time_p_f;
+    P.time_f_p = c.time_f_p; P.time1_p_f_p = c.time1_p_f_p; P.time2_p_f_p = c.time2_p_f_p;
+    P.time3_p_f_p = c.time3_p_f_p; P.time34_p_f_p = c.time34_p_f_p; P.time4_p_f_p = c.time4_p_f_p;
+    P.time45_p_f_p = c.time45_p_f_p; P.time5_p_f_p = c.time5_p_f_p; P.time1_f_p_f = c.time1_f_p_f;
+    P.time2_f_p_f = c.time2_f_p_f; P.time23_f_p_f = c.time23_f_p_f; P.time3_f_p_f = c.time3_f_p_f;
+    P.time34_f_p_f = c.time34_f_p_f; P.time4_f_p_f = c.time4_f_p_f; P.time45_f_p_f = c.time45_f_p_f;
+    P.time5_f_p_f = c.time5_f_p_f; P.i_fully_developed = c.i_fully_developed; P.j_fully_developed = c.j_fully_developed;
+    P.noise = c.noise; P.eps_len_d = c.eps_len_d;
+    P.convert_mol_to_Nm3 = c.convert_mol_to_Nm3; P.H_u_CH4 = c.H_u_CH4; P.H_u_H2 = c.H_u_H2; P.dt_water = c.dt_water;
+    P.cp_water = c.cp_water; P.rho_water = c.rho_water; P.Molar_mass_CO2 = c.Molar_mass_CO2;
+    P.Molar_mass_H2O = c.Molar_mass_H2O; P.h_H2O_evap = c.h_H2O_evap; P.eeg_el_price = c.eeg_el_price;
+    P.heat_price = c.heat_price; P.o2_price = c.o2_price; P.water_price = c.water_price;
+    P.min_load_electrolyzer = c.min_load_electrolyzer; P.max_h2_volumeflow = c.max_h2_volumeflow; P.eta_CHP = c.eta_CHP;
+    P.sim_step_d = (double)c.sim_step;
+    for (int q = 0; q < 6; ++q) P.prob_thre[q] = -1 + q * ((1.0 - (-1.0)) / 5);   // :151-155
+
+    // ---- observation layout: key-major blocks, each block start 16 B aligned ----
+    P.n_pad = round_up4(n_envs);
+    int64_t off = 0;
+    auto add_key = [&](const char* name, int dim, int is_int, int64_t elems) {
+        PtgObsKey k{};
+        std::snprintf(k.name, sizeof(k.name), "%s", name);
+        k.dim = dim; k.is_int32 = is_int; k.offset = off;
+        h->keys.push_back(k);
+        off += round_up4(elems);
+    };
+    P.off_win0 = off;
+    if (P.raw) {
+        add_key("Elec_Price", P.pa, 0, n_envs * P.pa);
+        P.off_win1 = 0;
+        P.off_gas = off; add_key("Gas_Price", 2, 0, n_envs * 2);
+        P.off_eua = off; add_key("EUA_Price", 2, 0, n_envs * 2);
+    } else {
+        add_key("Pot_Reward", P.pa, 0, n_envs * P.pa);
+        P.off_win1 = off; add_key("Part_Full", P.pa, 0, n_envs * P.pa);
+    }
+    P.off_scalar = off;
+    const char* scalar_names[9] = {"METH_STATUS", "T_CAT", "H2_in_MolarFlow", "CH4_syn_MolarFlow", "H2_res_MolarFlow",
+                                   "H2O_DE_MassFlow", "Elec_Heating", "Temp_hour_enc_sin", "Temp_hour_enc_cos"};
+    for (int q = 0; q < 9; ++q) add_key(scalar_names[q], 1, q == 0, n_envs);
+    P.obs_elems = off;
+
+    // ---- upload raw tables ----
+    int32_t ent = 0;
+    std::vector<double> tvals;
+    tvals.push_back(16.0);                                             // reset temperature, :117
+    for (int d = 0; d < PTG_N_DATASETS; ++d) {
+        const int64_t L = tables->op_rows[d];
+        PTG_TRY(h->upload(&B.rows[d], tables->op[d], (size_t)L * 7));
+        B.len[d] = (int32_t)L; B.ent_off[d] = ent;
+        P.ds_len[d] = (int32_t)L; P.ent_off[d] = ent;
+        ent += (int32_t)L + 1;
+        for (int64_t r = 0; r < L; ++r) tvals.push_back(tables->op[d][r * 7 + 1]);
+    }
+    std::sort(tvals.begin(), tvals.end());
+    tvals.erase(std::unique(tvals.begin(), tvals.end()), tvals.end());
+    if (tvals.size() >= (1u << 28)) { ptg_destroy(h); return fail(PTG_ERR_UNSUPPORTED, "too many distinct temperatures"); }
+    B.S = P.S; B.n_entries = ent; B.n_vals = (int32_t)tvals.size(); P.n_vals = B.n_vals;
+    PTG_TRY(h->upload(&B.vals, tvals.data(), tvals.size()));
+    h->d_vals = const_cast<double*>(B.vals);
+    B.t_cat_standby = c.t_cat_standby; B.t_cat_startup_cold = c.t_cat_startup_cold; B.t_cat_startup_hot = c.t_cat_startup_hot;
+    const double lo[6] = {c.T_l_b, c.h2_l_b, c.ch4_l_b, c.h2_res_l_b, c.h2o_l_b, c.heat_l_b};
+    const double hi[6] = {c.T_u_b, c.h2_u_b, c.ch4_u_b, c.h2_res_u_b, c.h2o_u_b, c.heat_u_b};
+    for (int q = 0; q < 6; ++q) { B.lo[q] = lo[q]; B.hi[q] = hi[q]; }
+
+    // ---- build the device tables ----
+    StepEntry* step_tab = nullptr;
+    PTG_TRY(h->alloc(&step_tab, (size_t)ent));
+    k_build_step_tab<<<blocks_for(ent, 128), 128>>>(B, step_tab);
+    int32_t* lut = nullptr;
+    PTG_TRY(h->alloc(&lut, (size_t)B.n_vals * PTG_N_ARGMIN));
+    k_build_argmin<<<dim3((unsigned)B.n_vals, PTG_N_ARGMIN), 256>>>(B, lut);
+    h->launches += 2;
+    P.step_tab = step_tab; P.argmin_lut = lut;
+
+    PTG_TRY(h->alloc(&h->d_err, 1));
+    PTG_TRY(cudaMemset(h->d_err, 0, sizeof(uint32_t)));
+    P.err = h->d_err;
+
+    const double* d_erb = nullptr;
+    PTG_TRY(h->upload(&d_erb, tables->e_r_b, (size_t)3 * P.pa * tables->n_hours));
+    float* hour_tab = nullptr;
+    PTG_TRY(h->alloc(&hour_tab, (size_t)tables->n_hours * P.nv * 4));
+    k_build_hour_tab<<<blocks_for(tables->n_hours, 128), 128>>>(d_erb, P.n_hours, P.pa, P.nv, P.raw,
+                                                              P.raw ? c.el_l_b : c.rew_l_b, P.raw ? c.el_u_b : c.rew_u_b,
+                                                              hour_tab, h->d_err);
+    P.hour_tab = reinterpret_cast<const float4*>(hour_tab);
+    P.pot0 = d_erb + (size_t)1 * P.pa * tables->n_hours;
+    P.pf0 = d_erb + (size_t)2 * P.pa * tables->n_hours;
+    const double* d_ge = nullptr;
+    PTG_TRY(h->upload(&d_ge, tables->g_e, (size_t)4 * tables->n_days));
+    DayRow* day_tab = nullptr;
+    PTG_TRY(h->alloc(&day_tab, (size_t)tables->n_days));
+    k_build_day_tab<<<blocks_for(tables->n_days, 128), 128>>>(d_ge, P.n_days, c.gas_l_b, c.gas_u_b, c.eua_l_b, c.eua_u_b, day_tab);
+    P.day_tab = day_tab;
+    ClockRow* clock_tab = nullptr;
+    PTG_TRY(h->alloc(&clock_tab, (size_t)c.eps_sim_steps + 1));
+    k_build_clock_tab<<<blocks_for(c.eps_sim_steps + 1, 128), 128>>>(c.eps_sim_steps + 1, c.sim_step, clock_tab);
+    P.clock_tab = clock_tab;
+    h->launches += 3;
+    if (tables->eps_ind) PTG_TRY(h->upload(&P.eps_ind, tables->eps_ind, (size_t)tables->n_eps_ind));
+    else P.eps_ind = nullptr;
+
+    // ziggurat tables
+    {
+        const uint64_t* ki = nullptr; const uint64_t* wi = nullptr; const uint64_t* fi = nullptr;
+        PTG_TRY(h->upload(&ki, PTG_ZIG_KI, 256));
+        PTG_TRY(h->upload(&wi, PTG_ZIG_WI_BITS, 256));
+        PTG_TRY(h->upload(&fi, PTG_ZIG_FI_BITS, 256));
+        P.zig.ki = ki; P.zig.wi = reinterpret_cast<const double*>(wi); P.zig.fi = reinterpret_cast<const double*>(fi);
+    }
+
+    PTG_TRY(cudaDeviceSynchronize());
+    PTG_TRY(cudaGetLastError());
+
+    // ---- reset constants: i = argmin |cooldown.T - 16| (:118), flows = cooldown[i, 2:7] (:120-122) ----
+    {
+        const int v16 = (int)(std::lower_bound(tvals.begin(), tvals.end(), 16.0) - tvals.begin());
+        int32_t i0 = 0;
+        PTG_TRY(cudaMemcpy(&i0, lut + (size_t)v16 * PTG_N_ARGMIN + 0, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        P.reset_i = i0;
+        const int flags = (16.0 <= c.t_cat_startup_cold ? PTG_TF_COLD : 0) | (16.0 >= c.t_cat_startup_hot ? PTG_TF_HOT : 0) |
+                          (16.0 <= c.t_cat_standby ? PTG_TF_SBUP : 0);
+        P.reset_tinfo = (v16 << 3) | flags;
+        const double* row = tables->op[PTG_DS_COOLDOWN] + (size_t)i0 * 7;
+        for (int q = 0; q < 5; ++q) P.reset_flow[q] = row[2 + q];
+        P.reset_norm[0] = (float)((16.0 - lo[0]) / (hi[0] - lo[0]));
+        for (int q = 0; q < 5; ++q) P.reset_norm[1 + q] = (float)((row[2 + q] - lo[1 + q]) / (hi[1 + q] - lo[1 + q]));
+        uint32_t e = 0;
+        PTG_TRY(cudaMemcpy(&e, h->d_err, sizeof(e), cudaMemcpyDeviceToHost));
+        if ((e & PTG_EBIT_PARTFULL) && !P.raw) {
+            ptg_destroy(h);
+            return fail(PTG_ERR_UNSUPPORTED, "e_r_b[2] (part_full) holds values other than -1, 0, 1");
+        }
+        PTG_TRY(cudaMemset(h->d_err, 0, sizeof(uint32_t)));
+    }
+
+    // ---- per-env state ----
+    const size_t n = (size_t)n_envs;
+    PTG_TRY(h->alloc(&P.core, n)); PTG_TRY(h->alloc(&P.tinfo, n)); PTG_TRY(h->alloc(&P.ep, n));
+    PTG_TRY(h->alloc(&P.ep_ret, n)); PTG_TRY(h->alloc(&P.ep_count, n)); PTG_TRY(h->alloc(&P.ep_start, n));
+    PTG_TRY(h->alloc(&P.nchg, n)); PTG_TRY(h->alloc(&P.rng_state, n)); PTG_TRY(h->alloc(&P.rng_inc, n));
+    PTG_TRY(h->alloc(&P.draws, n));
+    PTG_TRY(h->alloc(&P.fin_cnt, n)); PTG_TRY(h->alloc(&P.fin_ret_sum, n)); PTG_TRY(h->alloc(&P.fin_ret_sq, n));
+    PTG_TRY(h->alloc(&P.fin_len_sum, n)); PTG_TRY(h->alloc(&P.fin_min, n)); PTG_TRY(h->alloc(&P.fin_max, n));
+    PTG_TRY(h->alloc(&h->d_seeds, n)); PTG_TRY(h->alloc(&h->d_mask, n));
+    PTG_TRY(h->alloc(&h->d_partial, PTG_STATS_BLOCKS));
+    PTG_TRY(h->alloc(&h->d_state_i32, n * 13)); PTG_TRY(h->alloc(&h->d_state_i64, n)); PTG_TRY(h->alloc(&h->d_state_f64, n * 2));
+    P.tape = nullptr; P.tape_len = 0;
+    k_construct<<<blocks_for(n_envs, 256), 256>>>(P);
+    h->launches += 1;
+    PTG_TRY(cudaDeviceSynchronize());
+    PTG_TRY(cudaGetLastError());
+#undef PTG_TRY
+    *out = h;
+    return PTG_OK;
+}
+
+extern "C" void ptg_destroy(PtgHandle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// reset / step
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int ptg_reset(PtgHandle* h, const int64_t* seeds, const uint8_t* mask, const PtgIO* io, void* stream) {
+    if (!h || !io) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle/io");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PTG_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->P.n_envs;
+    const int64_t* d_seeds = nullptr;
+    const uint8_t* d_mask = nullptr;
+    if (seeds) {
+        PTG_CUDA(cudaMemcpyAsync(h->d_seeds, seeds, n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        d_seeds = h->d_seeds;
+    }
+    if (mask) {
+        PTG_CUDA(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, st));
+        d_mask = h->d_mask;
+    }
+    PTG_DISPATCH(launch_reset_t, h, d_seeds, d_mask, *io, st);
+    h->launches += 1;
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
+static int check_step_io(const PtgHandle* h, const void* actions, int adtype, const PtgIO* io) {
+    if (!h || !io || !actions) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle/io/actions");
+    if (!io->obs || !io->reward || !io->done) return fail(PTG_ERR_INVALID_ARGUMENT, "obs, reward and done buffers are required");
+    if (adtype < PTG_ACT_I64 || adtype > PTG_ACT_F32) return fail(PTG_ERR_INVALID_ARGUMENT, "unknown action dtype");
+    if (h->P.continuous && adtype != PTG_ACT_F32)
+        return fail(PTG_ERR_INVALID_ARGUMENT, "continuous action space needs float32 actions (Box(-1, 1, (1,), float32))");
+    return PTG_OK;
+}
+
+extern "C" int ptg_step(PtgHandle* h, const void* actions, int action_dtype, const PtgIO* io, void* stream) {
+    int rc = check_step_io(h, actions, action_dtype, io);
+    if (rc != PTG_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PTG_DISPATCH(launch_step_t, h, actions, action_dtype, *io, 1, st);
+    h->launches += 1;
+    h->total_steps += (double)h->P.n_envs;
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
+extern "C" int ptg_step_many(PtgHandle* h, const void* actions, int action_dtype, int32_t T, const PtgIO* io,
+                             void* stream) {
+    int rc = check_step_io(h, actions, action_dtype, io);
+    if (rc != PTG_OK) return rc;
+    if (T < 1) return fail(PTG_ERR_INVALID_ARGUMENT, "T must be >= 1");
+    if (io->terminal_obs || io->info || io->episode_return || io->episode_length)
+        return fail(PTG_ERR_INVALID_ARGUMENT, "ptg_step_many records only obs/reward/done");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PTG_DISPATCH(launch_step_t, h, actions, action_dtype, *io, (int)T, st);
+    h->launches += 1;
+    h->total_steps += (double)h->P.n_envs * T;
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
+extern "C" int ptg_set_noise_tape(PtgHandle* h, const double* tape_dev, int64_t tape_len) {
+    if (!h) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle");
+    if (tape_len < 0 || (tape_len > 0 && !tape_dev)) return fail(PTG_ERR_INVALID_ARGUMENT, "bad tape");
+    h->P.tape = tape_dev;
+    h->P.tape_len = tape_len;
+    return PTG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// state snapshot
+// ------------------------------------------------------------------------------------------------------------
+static StateDev state_dev(PtgHandle* h) {
+    const size_t n = (size_t)h->P.n_envs;
+    int32_t* b = h->d_state_i32;
+    StateDev s;
+    s.meth_state = b; s.i = b + n; s.j = b + 2 * n; s.k = b + 3 * n; s.hot_cold = b + 4 * n; s.standby_ds = b + 5 * n;
+    s.startup_ds = b + 6 * n; s.partial_ds = b + 7 * n; s.full_ds = b + 8 * n; s.current_action = b + 9 * n;
+    s.act_ep_h = b + 10 * n; s.act_ep_d = b + 11 * n; s.episode_count = b + 12 * n;
+    s.draws = h->d_state_i64; s.t_cat = h->d_state_f64; s.cum_reward = h->d_state_f64 + n;
+    return s;
+}
+
+extern "C" int ptg_get_state(PtgHandle* h, const PtgStateSoA* out) {
+    if (!h || !out) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle/state");
+    PTG_CUDA(cudaSetDevice(h->device));
+    PTG_CUDA(cudaDeviceSynchronize());
+    StateDev s = state_dev(h);
+    const size_t n = (size_t)h->P.n_envs;
+    k_state_unpack<<<blocks_for(h->P.n_envs, 256), 256>>>(h->P, s, h->d_vals);
+    h->launches += 1;
+    PTG_CUDA(cudaDeviceSynchronize());
+    int32_t* const dst32[13] = {out->meth_state, out->i, out->j, out->k, out->hot_cold, out->standby_ds, out->startup_ds,
+                                out->partial_ds, out->full_ds, out->current_action, out->act_ep_h, out->act_ep_d,
+                                out->episode_count};
+    for (int q = 0; q < 13; ++q)
+        if (dst32[q]) PTG_CUDA(cudaMemcpy(dst32[q], h->d_state_i32 + q * n, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (out->draws) PTG_CUDA(cudaMemcpy(out->draws, s.draws, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (out->t_cat) PTG_CUDA(cudaMemcpy(out->t_cat, s.t_cat, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (out->cum_reward) PTG_CUDA(cudaMemcpy(out->cum_reward, s.cum_reward, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return PTG_OK;
+}
+
+extern "C" int ptg_set_state(PtgHandle* h, const PtgStateSoA* in) {
+    if (!h || !in) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle/state");
+    const int32_t* const src32[13] = {in->meth_state, in->i, in->j, in->k, in->hot_cold, in->standby_ds, in->startup_ds,
+                                      in->partial_ds, in->full_ds, in->current_action, in->act_ep_h, in->act_ep_d,
+                                      in->episode_count};
+    for (int q = 0; q < 13; ++q) if (!src32[q]) return fail(PTG_ERR_INVALID_ARGUMENT, "ptg_set_state needs every field");
+    if (!in->draws || !in->t_cat || !in->cum_reward) return fail(PTG_ERR_INVALID_ARGUMENT, "ptg_set_state needs every field");
+    PTG_CUDA(cudaSetDevice(h->device));
+    PTG_CUDA(cudaDeviceSynchronize());
+    StateDev s = state_dev(h);
+    const size_t n = (size_t)h->P.n_envs;
+    // t_cat values must exist in the tables: verify on the host against the distinct-value list
+    std::vector<double> vals((size_t)h->B.n_vals);
+    PTG_CUDA(cudaMemcpy(vals.data(), h->d_vals, vals.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t e = 0; e < n; ++e)
+        if (!std::binary_search(vals.begin(), vals.end(), in->t_cat[e]))
+            return fail(PTG_ERR_INVALID_ARGUMENT, "ptg_set_state: t_cat is not a temperature of the operation tables");
+    for (int q = 0; q < 13; ++q)
+        PTG_CUDA(cudaMemcpy(h->d_state_i32 + q * n, src32[q], n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    PTG_CUDA(cudaMemcpy(s.draws, in->draws, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+    PTG_CUDA(cudaMemcpy(s.t_cat, in->t_cat, n * sizeof(double), cudaMemcpyHostToDevice));
+    PTG_CUDA(cudaMemcpy(s.cum_reward, in->cum_reward, n * sizeof(double), cudaMemcpyHostToDevice));
+    k_state_pack<<<blocks_for(h->P.n_envs, 256), 256>>>(h->P, s, h->B);
+    h->launches += 1;
+    PTG_CUDA(cudaDeviceSynchronize());
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// statistics / errors / introspection
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int ptg_episode_stats(PtgHandle* h, PtgEpisodeStats* stats_dev, int clear, void* stream) {
+    if (!h || !stats_dev) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle/stats");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    k_stats_partial<<<PTG_STATS_BLOCKS, 256, 0, st>>>(h->P, h->d_partial, clear);
+    k_stats_final<<<1, 256, 0, st>>>(h->d_partial, PTG_STATS_BLOCKS, h->total_steps, stats_dev);
+    h->launches += 2;
+    if (clear) h->total_steps = 0.0;
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
+extern "C" void ptg_stats_combine(const PtgEpisodeStats* per_rank, int n_ranks, PtgEpisodeStats* out) {
+    PtgEpisodeStats a{};
+    a.min_return = INFINITY; a.max_return = -INFINITY;
+    for (int r = 0; r < n_ranks; ++r) {          // fixed rank order: deterministic
+        a.count += per_rank[r].count; a.sum_return += per_rank[r].sum_return;
+        a.sum_return_sq += per_rank[r].sum_return_sq; a.sum_length += per_rank[r].sum_length;
+        a.total_steps += per_rank[r].total_steps;
+        a.min_return = std::min(a.min_return, per_rank[r].min_return);
+        a.max_return = std::max(a.max_return, per_rank[r].max_return);
+    }
+    *out = a;
+}
+
+extern "C" int ptg_poll_error(PtgHandle* h, void* stream) {
+    if (!h) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t e = 0;
+    PTG_CUDA(cudaMemcpyAsync(&e, h->d_err, sizeof(e), cudaMemcpyDeviceToHost, st));
+    PTG_CUDA(cudaStreamSynchronize(st));
+    if (e == 0) return PTG_OK;
+    PTG_CUDA(cudaMemsetAsync(h->d_err, 0, sizeof(uint32_t), st));
+    if (e & PTG_EBIT_ACTION) return fail(PTG_ERR_INVALID_ACTION, "invalid action - must be one of 0..4 [standby, cooldown, startup, partial_load, full_load]");
+    if (e & PTG_EBIT_RANGE) return fail(PTG_ERR_DATA_RANGE, "episode clock ran past the end of the market tables (the reference raises IndexError)");
+    if (e & PTG_EBIT_TAPE) return fail(PTG_ERR_NOISE_TAPE, "noise tape exhausted");
+    return fail(PTG_ERR_INVALID_ARGUMENT, "unknown device error bit");
+}
+
+extern "C" int ptg_obs_dim(const PtgHandle* h) { return h ? h->P.obs_dim : 0; }
+
+extern "C" int ptg_obs_layout(const PtgHandle* h, PtgObsKey* keys, int max_keys) {
+    if (!h) return 0;
+    const int n = (int)h->keys.size();
+    for (int q = 0; q < n && q < max_keys && keys; ++q) keys[q] = h->keys[q];
+    return n;
+}
+
+extern "C" int64_t ptg_obs_elems(const PtgHandle* h) { return h ? h->P.obs_elems : 0; }
+extern "C" int64_t ptg_num_envs(const PtgHandle* h) { return h ? h->P.n_envs : 0; }
+
+// Algorithmic HBM bytes of one env step through ptg_step (DESIGN.md "bytes per env-step"): action in; core int4,
+// tinfo, ep_ret read + written; ep read; observation, reward, done out.  Table rows are L2-resident and not counted.
+extern "C" int64_t ptg_bytes_per_env_step(const PtgHandle* h, int action_dtype) {
+    if (!h) return 0;
+    const int64_t act = action_dtype == PTG_ACT_I64 ? 8 : action_dtype == PTG_ACT_U8 ? 1 : 4;
+    const int64_t state_rd = 16 + 4 + 8 + 8, state_wr = 16 + 4 + 8;
+    return act + state_rd + state_wr + 4 * (int64_t)h->P.obs_dim + 4 + 1;
+}
+
+extern "C" int ptg_kernel_launches(const PtgHandle* h, int64_t* out) {
+    if (!h || !out) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle/out");
+    *out = h->launches;
+    return PTG_OK;
+}
+
+extern "C" const char* ptg_last_error(void) { return g_last_error.c_str(); }
+extern "C" int ptg_abi_version(void) { return PTG_ABI_VERSION; }

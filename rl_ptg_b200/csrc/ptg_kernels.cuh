@@ -1,0 +1,675 @@
+// ptg_kernels.cuh -- CUDA kernels of the batched PtG environment (sm_100a).
+//
+//   k_build_*      one-off table construction on the device (window means, argmin LUT, market rows, clock)
+//   k_construct    PTGEnv.__init__ for all envs
+//   k_reset        VecEnv.reset() / PTGEnv.reset(seed)
+//   k_step         VecEnv.step_wait(): T >= 1 env steps per launch, state in registers, SB3 auto-reset
+//   k_stats_*      deterministic two-stage reduction of finished-episode statistics (warp shuffles)
+//
+// The step kernel is HBM-bound streaming of per-env state + observation rows; the only gathers go to
+// L2-resident tables (step table 80 B/entry, hour row 16*NV B, day row 32 B, clock row 16 B).  The two
+// [n_envs, price_ahead] observation blocks are transposed through shared memory per warp so that every global
+// store is a coalesced 16-byte vector.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "ptg_device.cuh"
+
+// ------------------------------------------------------------------------------------------------------------
+// table construction
+// ------------------------------------------------------------------------------------------------------------
+struct BuildParams {
+    const double* rows[PTG_N_DATASETS];   // device copies of the raw tables, row-major [len][7]
+    int32_t len[PTG_N_DATASETS];
+    int32_t ent_off[PTG_N_DATASETS];
+    int32_t S;
+    int32_t n_entries;
+    const double* vals;                   // sorted distinct T values (incl. the reset temperature 16)
+    int32_t n_vals;
+    double t_cat_standby, t_cat_startup_cold, t_cat_startup_hot;
+    double lo[6], hi[6];                  // normalisation bounds: T, h2, ch4, h2_res, h2o, heat
+};
+
+// Virtual S-row window of _perform_sim_step (env/ptg_gym_env.py:525-557) starting at row s of table ds:
+// rows [s, L) of the table, then either the last row repeated (change_operation == False) or the first rows of
+// op1_start_p (the start-up tables, which are always stepped with change_operation == True, :386-388,:624).
+struct WindowView {
+    const double* head; int head_rows;      // rows s .. L-1 (may be 0)
+    const double* tail; int tail_stride;    // tail rows: stride 7 (hand-over) or 0 (repeat last row)
+    int n;                                  // total rows (== S except when the hand-over table is too short)
+    __device__ double at(int q, int col) const {
+        return q < head_rows ? head[(int64_t)q * 7 + col] : tail[(int64_t)(q - head_rows) * tail_stride + col];
+    }
+};
+
+// numpy's pairwise summation (np.add.reduce) over column `col` of the window, rows [lo, lo + n)
+__device__ double window_pairwise_sum(const WindowView& w, int col, int lo, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res += w.at(lo + i, col);
+        return res;
+    } else if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = w.at(lo + q, col);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] += w.at(lo + i + q, col);
+        }
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += w.at(lo + i, col);
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return window_pairwise_sum(w, col, lo, n2) + window_pairwise_sum(w, col, lo + n2, n - n2);
+    }
+}
+
+__device__ __forceinline__ int find_val(const double* vals, int n, double v) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (vals[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;    // exact match guaranteed by construction
+}
+
+__device__ __forceinline__ int tinfo_of(const BuildParams& B, double T) {
+    int flags = (T <= B.t_cat_startup_cold ? PTG_TF_COLD : 0) | (T >= B.t_cat_startup_hot ? PTG_TF_HOT : 0) |
+                (T <= B.t_cat_standby ? PTG_TF_SBUP : 0);
+    return (find_val(B.vals, B.n_vals, T) << 3) | flags;
+}
+
+__global__ void k_build_step_tab(const __grid_constant__ BuildParams B, StepEntry* out) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B.n_entries) return;
+    int ds = 0;
+#pragma unroll
+    for (int d = 1; d < PTG_N_DATASETS; ++d) if (g >= B.ent_off[d]) ds = d;
+    const int s = g - B.ent_off[ds], L = B.len[ds], S = B.S;
+    const bool handover = (ds == PTG_DS_STARTUP_COLD || ds == PTG_DS_STARTUP_HOT);
+    WindowView w;
+    w.head = B.rows[ds] + (int64_t)s * 7;
+    w.head_rows = min(S, L - s);
+    int ov = S - w.head_rows;                      // rows beyond the end of the table
+    if (handover && w.head_rows > 0) {             // tail = next_operation[:overhead]
+        w.tail = B.rows[PTG_DS_OP1_START_P];
+        w.tail_stride = 7;
+        ov = min(ov, B.len[PTG_DS_OP1_START_P]);
+    } else {                                       // tail = operation[-1] repeated (also: s == L, any table)
+        w.tail = B.rows[ds] + (int64_t)(L - 1) * 7;
+        w.tail_stride = 0;
+    }
+    w.n = w.head_rows + ov;
+    StepEntry e;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) e.mean[c] = window_pairwise_sum(w, 2 + c, 0, w.n) / (double)w.n;   // np.average
+    e.t_end = w.at(w.n - 1, 1);
+    e.norm[0] = (float)((e.t_end - B.lo[0]) / (B.hi[0] - B.lo[0]));
+#pragma unroll
+    for (int c = 0; c < 5; ++c) e.norm[1 + c] = (float)((e.mean[c] - B.lo[1 + c]) / (B.hi[1 + c] - B.lo[1 + c]));
+    e.tinfo = tinfo_of(B, e.t_end);
+    e._pad = 0;
+    out[g] = e;
+}
+
+// argmin LUT: lut[v][c] = first index of min |T_c[:] - vals[v]|  (np.abs(..).argmin(), :521-522)
+__global__ void k_build_argmin(const __grid_constant__ BuildParams B, int32_t* lut) {
+    const int v = blockIdx.x, c = blockIdx.y;
+    const int targets[PTG_N_ARGMIN] = {PTG_DS_COOLDOWN, PTG_DS_STANDBY_UP, PTG_DS_STANDBY_DOWN,
+                                       PTG_DS_STARTUP_COLD, PTG_DS_STARTUP_HOT, PTG_DS_OP1_START_P};
+    const int ds = targets[c], L = B.len[ds];
+    const double* tab = B.rows[ds];
+    const double t = B.vals[v];
+    double best = INFINITY;
+    int besti = 0x7fffffff;
+    for (int r = threadIdx.x; r < L; r += blockDim.x) {
+        double d = fabs(tab[(int64_t)r * 7 + 1] - t);
+        if (d < best) { best = d; besti = r; }      // ascending r per thread: first occurrence kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_down_sync(0xffffffffu, best, o);
+        int oi = __shfl_down_sync(0xffffffffu, besti, o);
+        if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    __shared__ double sb[32];
+    __shared__ int si[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sb[wid] = best; si[wid] = besti; }
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = blockDim.x >> 5;
+        best = lane < nw ? sb[lane] : INFINITY;
+        besti = lane < nw ? si[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_down_sync(0xffffffffu, best, o);
+            int oi = __shfl_down_sync(0xffffffffu, besti, o);
+            if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        if (lane == 0) lut[v * PTG_N_ARGMIN + c] = besti;
+    }
+}
+
+// hour rows: [pa fp32 window | ... | packed part_full (2 bits each) | el fp64] in nv 16-byte vectors
+__global__ void k_build_hour_tab(const double* e_r_b, int n_hours, int pa, int nv, int raw, double lo, double hi,
+                                 float* out, uint32_t* err) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_hours) return;
+    float* row = out + (int64_t)t * nv * 4;
+    const int src = raw ? 0 : 1;       // raw: el price window (:209) | mod: potential reward window (:208)
+    uint32_t bits = 0;
+    for (int a = 0; a < pa; ++a) {
+        double v = e_r_b[((int64_t)src * pa + a) * n_hours + t];
+        row[a] = (float)((v - lo) / (hi - lo));
+        double pf = e_r_b[((int64_t)2 * pa + a) * n_hours + t];
+        int code = (pf == -1.0) ? 0 : (pf == 0.0) ? 1 : (pf == 1.0) ? 2 : 3;
+        if (code == 3 && !raw) atomicOr(err, PTG_EBIT_PARTFULL);
+        bits |= (uint32_t)(code & 3) << (2 * a);
+    }
+    for (int a = pa; a < nv * 4 - 3; ++a) row[a] = 0.f;
+    row[nv * 4 - 3] = __uint_as_float(bits);
+    *reinterpret_cast<double*>(row + nv * 4 - 2) = e_r_b[t];          // e_r_b[0, 0, t]
+}
+
+__global__ void k_build_day_tab(const double* g_e, int n_days, double gas_lo, double gas_hi, double eua_lo,
+                                double eua_hi, DayRow* out) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_days) return;
+    DayRow r;
+    r.gas = g_e[d];
+    r.eua = g_e[(int64_t)2 * n_days + d];
+    r.gas_n0 = (float)((g_e[d] - gas_lo) / (gas_hi - gas_lo));                              // :210
+    r.gas_n1 = (float)((g_e[(int64_t)n_days + d] - gas_lo) / (gas_hi - gas_lo));
+    r.eua_n0 = (float)((g_e[(int64_t)2 * n_days + d] - eua_lo) / (eua_hi - eua_lo));        // :211
+    r.eua_n1 = (float)((g_e[(int64_t)3 * n_days + d] - eua_lo) / (eua_hi - eua_lo));
+    out[d] = r;
+}
+
+__global__ void k_build_clock_tab(int n, int sim_step, ClockRow* out) {
+    int k1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k1 >= n) return;
+    double clock_hours = (double)((long long)k1 * sim_step) / 3600;      // :442
+    double clock_days = clock_hours / 24;
+    ClockRow r;
+    r.sin_h = (float)sin(2 * 3.141592653589793 * clock_hours);            // :449-450
+    r.cos_h = (float)cos(2 * 3.141592653589793 * clock_hours);
+    r.h_step = (int)floor(clock_hours);
+    r.d_step = (int)floor(clock_days);
+    out[k1] = r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// observation emission
+// ------------------------------------------------------------------------------------------------------------
+struct ObsRegs {            // what one env contributes to the observation, in registers
+    int status;
+    float norm[6];
+    float sin_h, cos_h;
+};
+
+// Coalesced store of one [n_envs, pa] block: per-warp transpose through shared memory, 16-byte global stores.
+template <int NV>
+__device__ __forceinline__ void store_window_block(float* __restrict__ dst, float* sm, const float (&w)[4 * NV],
+                                                   int pa, int lane, int64_t warp_env0, int nvalid) {
+#pragma unroll
+    for (int a = 0; a < 4 * NV; ++a)
+        if (a < pa) sm[lane * pa + a] = w[a];
+    __syncwarp();
+    float* g = dst + warp_env0 * pa;
+    if (nvalid == 32) {
+        const float4* s4 = reinterpret_cast<const float4*>(sm);
+        float4* g4 = reinterpret_cast<float4*>(g);
+        for (int idx = lane; idx < 8 * pa; idx += 32) g4[idx] = s4[idx];
+    } else {
+        for (int idx = lane; idx < nvalid * pa; idx += 32) g[idx] = sm[idx];
+    }
+    __syncwarp();
+}
+
+template <int NV, bool MOD>
+__device__ __forceinline__ void emit_obs(const DevParams& P, float* __restrict__ obs, float* sm, int64_t e,
+                                         bool active, int lane, int64_t warp_env0, int nvalid,
+                                         const float4 (&hrow)[NV], const DayRow& day, const ObsRegs& o) {
+    float w[4 * NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { w[4 * v] = hrow[v].x; w[4 * v + 1] = hrow[v].y; w[4 * v + 2] = hrow[v].z; w[4 * v + 3] = hrow[v].w; }
+    store_window_block<NV>(obs + P.off_win0, sm, w, P.pa, lane, warp_env0, nvalid);
+    if (MOD) {
+        const uint32_t bits = __float_as_uint(w[4 * NV - 3]);
+#pragma unroll
+        for (int a = 0; a < 4 * NV; ++a) w[a] = (float)((bits >> (2 * a)) & 3u) - 1.0f;     // Part_Full, :239
+        store_window_block<NV>(obs + P.off_win1, sm, w, P.pa, lane, warp_env0, nvalid);
+    }
+    if (!active) return;
+    if (!MOD) {
+        reinterpret_cast<float2*>(obs + P.off_gas)[e] = make_float2(day.gas_n0, day.gas_n1);
+        reinterpret_cast<float2*>(obs + P.off_eua)[e] = make_float2(day.eua_n0, day.eua_n1);
+    }
+    float* sc = obs + P.off_scalar + e;
+    sc[0] = __int_as_float(o.status);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) sc[(1 + q) * P.n_pad] = o.norm[q];
+    sc[7 * P.n_pad] = o.sin_h;
+    sc[8 * P.n_pad] = o.cos_h;
+}
+
+// Snapshot of one env's observation inputs, built only inside the rare branches that call the noinline helpers
+// below (so the hot path keeps hrow/day/o in registers instead of addressable local memory).
+template <int NV>
+struct ObsSnap {
+    float4 hrow[NV];
+    DayRow day;
+    ObsRegs o;
+};
+template <int NV>
+__device__ __forceinline__ ObsSnap<NV> make_snap(const float4 (&hrow)[NV], const DayRow& day, const ObsRegs& o) {
+    ObsSnap<NV> s;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s.hrow[v] = hrow[v];
+    s.day = day; s.o = o;
+    return s;
+}
+
+// Scalar (uncoalesced) emission of one env's observation -- terminal observations only (rare).
+template <int NV, bool MOD>
+__device__ __noinline__ void emit_obs_scalar(const DevParams& P, float* __restrict__ obs, int64_t e,
+                                             const ObsSnap<NV> snap) {
+    const float* w = reinterpret_cast<const float*>(snap.hrow);
+    const DayRow& day = snap.day;
+    const ObsRegs& o = snap.o;
+    for (int a = 0; a < P.pa; ++a) obs[P.off_win0 + e * P.pa + a] = w[a];
+    if (MOD) {
+        const uint32_t bits = __float_as_uint(w[4 * NV - 3]);
+        for (int a = 0; a < P.pa; ++a) obs[P.off_win1 + e * P.pa + a] = (float)((bits >> (2 * a)) & 3u) - 1.0f;
+    } else {
+        obs[P.off_gas + 2 * e] = day.gas_n0; obs[P.off_gas + 2 * e + 1] = day.gas_n1;
+        obs[P.off_eua + 2 * e] = day.eua_n0; obs[P.off_eua + 2 * e + 1] = day.eua_n1;
+    }
+    float* sc = obs + P.off_scalar + e;
+    sc[0] = __int_as_float(o.status);
+    for (int q = 0; q < 6; ++q) sc[(1 + q) * P.n_pad] = o.norm[q];
+    sc[7 * P.n_pad] = o.sin_h;
+    sc[8 * P.n_pad] = o.cos_h;
+}
+
+template <int NV>
+__device__ __forceinline__ void load_hour_row(const DevParams& P, int t_hour, float4 (&hrow)[NV]) {
+    const float4* src = P.hour_tab + (int64_t)t_hour * NV;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) hrow[v] = __ldg(src + v);
+}
+
+__device__ __forceinline__ DayRow load_day_row(const DevParams& P, int t_day) {
+    const int4* src = reinterpret_cast<const int4*>(P.day_tab + t_day);
+    int4 a = __ldg(src), b = __ldg(src + 1);
+    DayRow d;
+    d.gas = __hiloint2double(a.y, a.x); d.eua = __hiloint2double(a.w, a.z);
+    d.gas_n0 = __int_as_float(b.x); d.gas_n1 = __int_as_float(b.y); d.eua_n0 = __int_as_float(b.z); d.eua_n1 = __int_as_float(b.w);
+    return d;
+}
+
+template <int NV>
+__device__ __forceinline__ double hour_row_el(const float4 (&hrow)[NV]) {
+    return __hiloint2double(__float_as_int(hrow[NV - 1].w), __float_as_int(hrow[NV - 1].z));
+}
+
+__device__ __forceinline__ void clamp_market_index(const DevParams& P, int& t_hour, int& t_day) {
+    if (t_hour >= P.n_hours || t_day >= P.n_days || t_hour < 0 || t_day < 0) {
+        atomicOr(P.err, PTG_EBIT_RANGE);       // the reference raises IndexError here
+        t_hour = max(0, min(t_hour, P.n_hours - 1));
+        t_day = max(0, min(t_day, P.n_days - 1));
+    }
+}
+
+// _get_info, :251-278, feature-major fp64 [24][n_envs]
+struct InfoSnap {
+    int k, t_hour, state, cur_action, hot_cold;
+    double el, gas, eua, t_cat, flow[5], cum_rew;
+    RewardParts r;
+};
+__device__ __noinline__ void write_info(const DevParams& P, double* info, int64_t e, const InfoSnap s) {
+    const int64_t n = P.n_envs;
+    double* f = info + e;
+    const int k = s.k, t_hour = s.t_hour;
+    const double t_cat = s.t_cat, cum_rew = s.cum_rew;
+    const double* flow = s.flow;
+    const RewardParts& r = s.r;
+    f[0 * n] = k;
+    f[1 * n] = s.el;
+    f[2 * n] = s.gas;
+    f[3 * n] = s.eua;
+    f[4 * n] = s.state;
+    f[5 * n] = s.cur_action;
+    f[6 * n] = s.hot_cold;
+    f[7 * n] = t_cat;
+    f[8 * n] = flow[0]; f[9 * n] = flow[1]; f[10 * n] = flow[3]; f[11 * n] = flow[4];
+    f[12 * n] = r.ch4_rev; f[13 * n] = r.steam_rev; f[14 * n] = r.o2_rev; f[15 * n] = r.eua_rev; f[16 * n] = r.chp_rev;
+    f[17 * n] = -r.heat_cost; f[18 * n] = -r.ely_cost; f[19 * n] = -r.water_cost;
+    f[20 * n] = r.rew;
+    f[21 * n] = cum_rew;
+    f[22 * n] = P.pot0[t_hour];
+    f[23 * n] = P.pf0[t_hour];
+}
+
+// _initialize_op_rew (:105-138) + episode offsets; returns the reset (core, tinfo, ep)
+__device__ __forceinline__ void env_reset_state(const DevParams& P, int64_t e, int32_t m_count, int4& core,
+                                                int32_t& tinfo, int2& ep, Meta& m) {
+    int ep_h, ep_d;
+    episode_offsets(P, e, m_count, ep_h, ep_d);
+    ep = make_int2(ep_h, ep_d);
+    m.state = PTG_COOLDOWN; m.hot_cold = 0; m.sb_up = 0; m.su_hot = 0;
+    m.part_ds = PTG_DS_OP1_START_P; m.full_ds = PTG_DS_OP2_START_F;
+    // current_action is NOT touched by reset() (only by __init__, :143)
+    core = make_int4(P.reset_i, 0, 0, (int)meta_pack(m));
+    tinfo = P.reset_tinfo;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// constructor / reset
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_construct(const __grid_constant__ DevParams P) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.n_envs) return;
+    const int64_t gid = P.env_id_offset + e;
+    // The reference's generator is unseeded until reset(seed=...) (gymnasium); we start every env from
+    // SeedSequence(global id) so that an unseeded run is still reproducible.
+    Pcg64 g = pcg64_from_seed((uint64_t)gid);
+    P.rng_state[e] = make_ulonglong2(g.s_hi, g.s_lo);
+    P.rng_inc[e] = make_ulonglong2(g.i_hi, g.i_lo);
+    P.draws[e] = 0;
+    if (P.schedule_mode == PTG_SCHED_SUBPROC) {
+        // :43-44 draws ep_index from an UNSEEDED generator per worker process; here: a fixed stream per global id
+        Pcg64 h = pcg64_from_seed(0x5eed0000ull + (uint64_t)gid);
+        P.ep_start[e] = (int32_t)(pcg64_next64(h) % (uint64_t)max(1, P.n_eps_ind > 0 ? P.n_eps_ind : 1));
+    } else {
+        P.ep_start[e] = 0;
+    }
+    Meta m;
+    m.cur_action = PTG_COOLDOWN;     // :143
+    int4 core; int32_t tinfo; int2 ep;
+    env_reset_state(P, e, 0, core, tinfo, ep, m);
+    P.core[e] = core; P.tinfo[e] = tinfo; P.ep[e] = ep;
+    P.ep_ret[e] = 0.0; P.ep_count[e] = 0;
+    if (P.has_penalty) P.nchg[e] = 0;
+    P.fin_cnt[e] = 0; P.fin_ret_sum[e] = 0.0; P.fin_ret_sq[e] = 0.0; P.fin_len_sum[e] = 0.0;
+    P.fin_min[e] = INFINITY; P.fin_max[e] = -INFINITY;
+}
+
+template <int NV, bool MOD>
+__global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ DevParams P, const int64_t* seeds,
+                                                     const uint8_t* mask, PtgIO io) {
+    __shared__ __align__(16) float stage[PTG_BLOCK / 32][32 * 4 * NV];
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t warp_env0 = e - lane;
+    const int nvalid = (int)min((int64_t)32, P.n_envs - warp_env0);
+    const bool active = e < P.n_envs;
+    const bool doit = active && (mask == nullptr || mask[e]);
+    // masked reset: only the selected envs write; the window blocks go through the scalar path then
+    float4 hrow[NV];
+    DayRow day = {};
+    ObsRegs o = {};
+#pragma unroll
+    for (int v = 0; v < NV; ++v) hrow[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int t_hour = 0, t_day = 0;
+    Meta m = {};
+    if (doit) {
+        if (seeds != nullptr && seeds[e] >= 0) {          // gymnasium Env.reset(seed=...)
+            Pcg64 g = pcg64_from_seed((uint64_t)seeds[e]);
+            P.rng_state[e] = make_ulonglong2(g.s_hi, g.s_lo);
+            P.rng_inc[e] = make_ulonglong2(g.i_hi, g.i_lo);
+            P.draws[e] = 0;
+        }
+        m = meta_unpack((uint32_t)P.core[e].w);
+        const int32_t mc = P.ep_count[e] + 1;
+        int4 core; int32_t tinfo; int2 ep;
+        env_reset_state(P, e, mc, core, tinfo, ep, m);
+        P.core[e] = core; P.tinfo[e] = tinfo; P.ep[e] = ep; P.ep_count[e] = mc; P.ep_ret[e] = 0.0;
+        if (P.has_penalty) P.nchg[e] = 0;
+        t_hour = ep.x; t_day = ep.y;
+        clamp_market_index(P, t_hour, t_day);
+        load_hour_row<NV>(P, t_hour, hrow);
+        day = load_day_row(P, t_day);
+        o.status = PTG_COOLDOWN;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) o.norm[q] = P.reset_norm[q];
+        o.sin_h = 0.0f; o.cos_h = 1.0f;                   // math.sin(0), math.cos(0), :102-103
+    }
+    if (io.obs != nullptr) {
+        if (mask == nullptr) emit_obs<NV, MOD>(P, io.obs, stage[wid], e, active, lane, warp_env0, nvalid, hrow, day, o);
+        else if (doit) emit_obs_scalar<NV, MOD>(P, io.obs, e, make_snap<NV>(hrow, day, o));
+    }
+    if (doit && io.info != nullptr) {
+        InfoSnap s = {};
+        s.k = 0; s.t_hour = t_hour; s.state = m.state; s.cur_action = m.cur_action; s.hot_cold = m.hot_cold;
+        s.el = hour_row_el<NV>(hrow); s.gas = day.gas; s.eua = day.eua; s.t_cat = 16.0; s.cum_rew = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) s.flow[q] = P.reset_flow[q];
+        write_info(P, io.info, e, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// step
+// ------------------------------------------------------------------------------------------------------------
+template <int NV, bool MOD>
+__global__ void __launch_bounds__(PTG_BLOCK) k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions,
+                                                    int adtype, PtgIO io, int T) {
+    __shared__ __align__(16) float stage[PTG_BLOCK / 32][32 * 4 * NV];
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t warp_env0 = e - lane;
+    if (warp_env0 >= P.n_envs) return;                  // whole warp out of range
+    const int nvalid = (int)min((int64_t)32, P.n_envs - warp_env0);
+    const bool active = e < P.n_envs;
+    const int64_t le = active ? e : P.n_envs - 1;       // tail lanes shadow the last env (no stores)
+
+    int4 core = P.core[le];
+    int32_t tinfo = P.tinfo[le];
+    int2 ep = P.ep[le];
+    double ep_ret = P.ep_ret[le];
+    Meta m = meta_unpack((uint32_t)core.w);
+    int i = core.x, j = core.y, k = core.z;
+
+    for (int t = 0; t < T; ++t) {
+        float4 hrow[NV];
+        DayRow day;
+        ObsRegs o;
+        float reward = 0.f;
+        int done = 0;
+        if (active) {
+            const int action = decode_action(P, actions, adtype, (int64_t)t * P.n_envs + e, m.cur_action);
+            const int prev_state = m.state;
+            const int ent = plant_transition(P, e, action, i, j, m, tinfo);
+            // step-table entry: 5 x 16 B
+            const int4* ep4 = reinterpret_cast<const int4*>(P.step_tab + ent);
+            const int4 q0 = __ldg(ep4), q1 = __ldg(ep4 + 1), q2 = __ldg(ep4 + 2), q3 = __ldg(ep4 + 3), q4 = __ldg(ep4 + 4);
+            double mean[5];
+            mean[0] = __hiloint2double(q0.y, q0.x); mean[1] = __hiloint2double(q0.w, q0.z);
+            mean[2] = __hiloint2double(q1.y, q1.x); mean[3] = __hiloint2double(q1.w, q1.z);
+            mean[4] = __hiloint2double(q2.y, q2.x);
+            const double t_end = __hiloint2double(q2.w, q2.z);
+            o.norm[0] = __int_as_float(q3.x); o.norm[1] = __int_as_float(q3.y); o.norm[2] = __int_as_float(q3.z);
+            o.norm[3] = __int_as_float(q3.w); o.norm[4] = __int_as_float(q4.x); o.norm[5] = __int_as_float(q4.y);
+            tinfo = q4.z;
+            // clock + market rows of the NEW hour/day (:442-447)
+            const int4 c4 = __ldg(reinterpret_cast<const int4*>(P.clock_tab + (k + 1)));
+            o.sin_h = __int_as_float(c4.x); o.cos_h = __int_as_float(c4.y);
+            int t_hour = ep.x + c4.z, t_day = ep.y + c4.w;
+            clamp_market_index(P, t_hour, t_day);
+            load_hour_row<NV>(P, t_hour, hrow);
+            day = load_day_row(P, t_day);
+            o.status = m.state;
+            // reward (:463-468)
+            RewardParts r;
+            const int state_change = (prev_state != m.state);
+            reward_parts(P, mean, hour_row_el<NV>(hrow), day.gas, day.eua, state_change, r);
+            ep_ret += r.rew;
+            reward = (float)r.rew;
+            uint32_t nchg = 0;
+            if (P.has_penalty) { nchg = P.nchg[e] + (uint32_t)state_change; P.nchg[e] = nchg; }
+            done = (k == P.eps_sim_steps - 6);            // :508-511 (k before the increment)
+            if (io.info != nullptr && P.eval_mode && T == 1) {
+                InfoSnap s;
+                s.k = k; s.t_hour = t_hour; s.state = m.state; s.cur_action = m.cur_action; s.hot_cold = m.hot_cold;
+                s.el = hour_row_el<NV>(hrow); s.gas = day.gas; s.eua = day.eua; s.t_cat = t_end;
+                s.cum_rew = ep_ret + (double)nchg * P.penalty;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) s.flow[q] = mean[q];
+                s.r = r;
+                write_info(P, io.info, e, s);
+            }
+            k += 1;
+            if (done) {                                   // SB3 auto-reset (DummyVecEnv.step_wait)
+                if (T == 1) {
+                    if (io.terminal_obs != nullptr) emit_obs_scalar<NV, MOD>(P, io.terminal_obs, e, make_snap<NV>(hrow, day, o));
+                    if (io.episode_return != nullptr) io.episode_return[e] = ep_ret;
+                    if (io.episode_length != nullptr) io.episode_length[e] = k;
+                }
+                P.fin_cnt[e] += 1;
+                P.fin_ret_sum[e] += ep_ret;
+                P.fin_ret_sq[e] += ep_ret * ep_ret;
+                P.fin_len_sum[e] += (double)k;
+                P.fin_min[e] = fmin(P.fin_min[e], ep_ret);
+                P.fin_max[e] = fmax(P.fin_max[e], ep_ret);
+                const int32_t mc = P.ep_count[e] + 1;
+                P.ep_count[e] = mc;
+                env_reset_state(P, e, mc, core, tinfo, ep, m);
+                P.ep[e] = ep;
+                if (P.has_penalty) P.nchg[e] = 0;
+                i = core.x; j = 0; k = 0; ep_ret = 0.0;
+                t_hour = ep.x; t_day = ep.y;
+                clamp_market_index(P, t_hour, t_day);
+                load_hour_row<NV>(P, t_hour, hrow);
+                day = load_day_row(P, t_day);
+                o.status = PTG_COOLDOWN;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) o.norm[q] = P.reset_norm[q];
+                o.sin_h = 0.0f; o.cos_h = 1.0f;
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) hrow[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            day = DayRow{};
+            o = ObsRegs{};
+        }
+        float* obs_t = io.obs + (int64_t)t * P.obs_elems;
+        emit_obs<NV, MOD>(P, obs_t, stage[wid], e, active, lane, warp_env0, nvalid, hrow, day, o);
+        if (active) {
+            io.reward[(int64_t)t * P.n_envs + e] = reward;
+            io.done[(int64_t)t * P.n_envs + e] = (uint8_t)done;
+        }
+    }
+    if (active) {
+        P.core[e] = make_int4(i, j, k, (int)meta_pack(m));
+        P.tinfo[e] = tinfo;
+        P.ep_ret[e] = ep_ret;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// episode statistics: deterministic two-stage reduction
+// ------------------------------------------------------------------------------------------------------------
+struct StatAcc { double cnt, sum, sq, len, mn, mx; };
+
+__device__ __forceinline__ StatAcc stat_combine(const StatAcc& a, const StatAcc& b) {
+    return StatAcc{a.cnt + b.cnt, a.sum + b.sum, a.sq + b.sq, a.len + b.len, fmin(a.mn, b.mn), fmax(a.mx, b.mx)};
+}
+__device__ __forceinline__ StatAcc stat_shfl_down(const StatAcc& a, int o) {
+    return StatAcc{__shfl_down_sync(0xffffffffu, a.cnt, o), __shfl_down_sync(0xffffffffu, a.sum, o),
+                   __shfl_down_sync(0xffffffffu, a.sq, o), __shfl_down_sync(0xffffffffu, a.len, o),
+                   __shfl_down_sync(0xffffffffu, a.mn, o), __shfl_down_sync(0xffffffffu, a.mx, o)};
+}
+__device__ __forceinline__ StatAcc stat_block_reduce(StatAcc a) {
+    __shared__ StatAcc sm[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = stat_combine(a, stat_shfl_down(a, o));
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = a;
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    a = (threadIdx.x < nw) ? sm[threadIdx.x] : StatAcc{0, 0, 0, 0, INFINITY, -INFINITY};
+    if (wid == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a = stat_combine(a, stat_shfl_down(a, o));
+    }
+    return a;   // valid in thread 0
+}
+
+#define PTG_STATS_BLOCKS 592   // 4 x 148 SMs
+
+__global__ void k_stats_partial(const __grid_constant__ DevParams P, StatAcc* partial, int clear) {
+    StatAcc a{0, 0, 0, 0, INFINITY, -INFINITY};
+    // fixed env -> thread assignment (blocked ranges) so that the summation order never depends on timing
+    const int64_t per_block = (P.n_envs + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = per_block * blockIdx.x, hi = min(P.n_envs, lo + per_block);
+    for (int64_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+        const int c = P.fin_cnt[e];
+        if (c > 0) {
+            a = stat_combine(a, StatAcc{(double)c, P.fin_ret_sum[e], P.fin_ret_sq[e], P.fin_len_sum[e], P.fin_min[e],
+                                        P.fin_max[e]});
+            if (clear) {
+                P.fin_cnt[e] = 0; P.fin_ret_sum[e] = 0.0; P.fin_ret_sq[e] = 0.0; P.fin_len_sum[e] = 0.0;
+                P.fin_min[e] = INFINITY; P.fin_max[e] = -INFINITY;
+            }
+        }
+    }
+    a = stat_block_reduce(a);
+    if (threadIdx.x == 0) partial[blockIdx.x] = a;
+}
+
+__global__ void k_stats_final(const StatAcc* partial, int n_partial, double total_steps, PtgEpisodeStats* out) {
+    StatAcc a{0, 0, 0, 0, INFINITY, -INFINITY};
+    for (int q = threadIdx.x; q < n_partial; q += blockDim.x) a = stat_combine(a, partial[q]);
+    a = stat_block_reduce(a);
+    if (threadIdx.x == 0) {
+        out->count = a.cnt; out->sum_return = a.sum; out->sum_return_sq = a.sq; out->sum_length = a.len;
+        out->min_return = a.mn; out->max_return = a.mx; out->total_steps = total_steps; out->_reserved = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// state snapshot helpers (get/set state): unpack to / pack from plain SoA int32 arrays on the device
+// ------------------------------------------------------------------------------------------------------------
+struct StateDev {
+    int32_t *meth_state, *i, *j, *k, *hot_cold, *standby_ds, *startup_ds, *partial_ds, *full_ds, *current_action,
+            *act_ep_h, *act_ep_d, *episode_count;
+    int64_t* draws;
+    double *t_cat, *cum_reward;
+};
+
+__global__ void k_state_unpack(const __grid_constant__ DevParams P, StateDev s, const double* vals) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.n_envs) return;
+    const int4 c = P.core[e];
+    const Meta m = meta_unpack((uint32_t)c.w);
+    s.meth_state[e] = m.state; s.i[e] = c.x; s.j[e] = c.y; s.k[e] = c.z; s.hot_cold[e] = m.hot_cold;
+    s.standby_ds[e] = m.sb_up ? PTG_DS_STANDBY_UP : PTG_DS_STANDBY_DOWN;
+    s.startup_ds[e] = m.su_hot ? PTG_DS_STARTUP_HOT : PTG_DS_STARTUP_COLD;
+    s.partial_ds[e] = m.part_ds; s.full_ds[e] = m.full_ds; s.current_action[e] = m.cur_action;
+    const int2 ep = P.ep[e];
+    s.act_ep_h[e] = ep.x; s.act_ep_d[e] = ep.y; s.episode_count[e] = P.ep_count[e];
+    s.draws[e] = P.draws[e];
+    s.t_cat[e] = vals[P.tinfo[e] >> 3];
+    s.cum_reward[e] = P.ep_ret[e];
+}
+
+__global__ void k_state_pack(const __grid_constant__ DevParams P, StateDev s, const BuildParams B) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.n_envs) return;
+    Meta m;
+    m.state = s.meth_state[e]; m.hot_cold = s.hot_cold[e];
+    m.sb_up = (s.standby_ds[e] == PTG_DS_STANDBY_UP); m.su_hot = (s.startup_ds[e] == PTG_DS_STARTUP_HOT);
+    m.part_ds = s.partial_ds[e]; m.full_ds = s.full_ds[e]; m.cur_action = s.current_action[e];
+    P.core[e] = make_int4(s.i[e], s.j[e], s.k[e], (int)meta_pack(m));
+    P.ep[e] = make_int2(s.act_ep_h[e], s.act_ep_d[e]);
+    P.ep_count[e] = s.episode_count[e];
+    P.draws[e] = s.draws[e];
+    P.tinfo[e] = tinfo_of(B, s.t_cat[e]);        // t_cat must be a temperature present in the tables (or 16)
+    P.ep_ret[e] = s.cum_reward[e];
+}

@@ -1,0 +1,453 @@
+"""``PtGVecEnv`` -- the batched PtG environment behind the Stable-Baselines3 ``VecEnv`` interface.
+
+Drop-in for what ``create_vec_envs`` builds in the reference (``src/rl_utils.py:448-500``):
+``VecNormalize(make_vec_env('PtGEnv-v0', n_envs, seed, vec_env_cls, env_kwargs=dict(dict_input=...,
+train_or_eval=..., render_mode="None")), norm_obs=False)`` minus the reward normalisation -- i.e. N ``PTGEnv``
+instances (``env/ptg_gym_env.py:23``) + ``Monitor`` + ``DummyVecEnv`` auto-reset, all stepped by ONE CUDA
+kernel launch per ``step()``.
+
+* constructor: the same flat ``dict_input`` the reference env takes (``src/rl_utils.py:337-405``)
+* ``reset() / step_async() / step_wait() / step() / seed() / close() / get_attr() / set_attr() / env_method() /
+  env_is_wrapped() / get_images() / render()`` with SB3 semantics (numpy in, numpy out; on ``done`` the
+  returned obs is the reset obs, ``infos[i]["terminal_observation"]`` the last obs, ``infos[i]["episode"]``
+  the Monitor record, ``infos[i]["TimeLimit.truncated"] = False``)
+* ``step_tensor() / reset_tensor() / rollout_tensor()``: the same on CUDA tensors with zero host copies
+* ``episode_stats()``: finished-episode statistics, combined across ranks when torch.distributed is initialised
+
+There is no CPU fallback: constructing this class needs a CUDA device and the built ``libptg_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Any, Sequence
+
+import numpy as np
+import torch
+
+from . import _abi, _lib, spaces
+
+try:  # pragma: no cover - SB3 is not installed in the build container
+    from stable_baselines3.common.vec_env.base_vec_env import VecEnv as _SB3VecEnv  # type: ignore
+except ModuleNotFoundError:
+    _SB3VecEnv = None
+
+_NOISE = {"numpy": _abi.NOISE_NUMPY, "tape": _abi.NOISE_TAPE, "off": _abi.NOISE_OFF}
+_TORCH_ACT = {torch.int64: _abi.ACT_I64, torch.int32: _abi.ACT_I32, torch.uint8: _abi.ACT_U8,
+              torch.float32: _abi.ACT_F32}
+
+
+def shard_range(n_envs_global: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous env-id range ``[lo, hi)`` owned by ``rank``; sizes differ by at most one."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, rem = divmod(int(n_envs_global), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class _VecEnvBase:
+    """Minimal SB3 ``VecEnv`` contract, used when stable_baselines3 is not importable."""
+
+    def __init__(self, num_envs, observation_space, action_space):
+        self.num_envs = num_envs
+        self.observation_space = observation_space
+        self.action_space = action_space
+        self.reset_infos = [{} for _ in range(num_envs)]
+        self._seeds = [None for _ in range(num_envs)]
+        self._options = [{} for _ in range(num_envs)]
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def _reset_seeds(self):
+        self._seeds = [None for _ in range(self.num_envs)]
+
+    def _reset_options(self):
+        self._options = [{} for _ in range(self.num_envs)]
+
+    def set_options(self, options=None):
+        pass
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def _get_indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, int):
+            return [indices]
+        return indices
+
+
+_Base = _SB3VecEnv if _SB3VecEnv is not None else _VecEnvBase
+
+
+class PtGVecEnv(_Base):
+    metadata = {"render_modes": ["None"]}
+
+    def __init__(self, dict_input: dict, n_envs: int, train_or_eval: str = "train", render_mode: str = "None",
+                 seed: int | None = None, device: str | torch.device = "cuda:0", noise: str = "numpy",
+                 env_id_offset: int = 0, n_envs_global: int | None = None, obs_dtype=np.float32,
+                 info_limit: int = 4096):
+        if noise not in _NOISE:
+            raise ValueError(f"noise must be one of {sorted(_NOISE)}")
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("PtGVecEnv needs a CUDA device; there is no CPU fallback")
+        self._L = _lib.load()
+        self.train_or_eval = train_or_eval
+        self.render_mode = render_mode
+        self.obs_dtype = np.dtype(obs_dtype)
+        self.info_limit = info_limit
+        self.n_envs_global = int(n_envs_global if n_envs_global is not None else n_envs)
+        self.env_id_offset = int(env_id_offset)
+        self.cfg = _abi.config_from_kwargs(dict_input, train_or_eval, _NOISE[noise])
+        tables, keep = _abi.tables_from_kwargs(dict_input, self.cfg.price_ahead)
+        self.raw_modified = dict_input["raw_modified"]
+        self.action_type = dict_input["action_type"]
+        obs_space = spaces.observation_space(self.raw_modified, self.cfg.price_ahead)
+        act_space = spaces.action_space(self.action_type)
+        if _SB3VecEnv is not None:   # pragma: no cover
+            super().__init__(int(n_envs), obs_space, act_space)
+        else:
+            _VecEnvBase.__init__(self, int(n_envs), obs_space, act_space)
+
+        h = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        with torch.cuda.device(dev_index):
+            _lib.check(self._L.ptg_create(C.byref(self.cfg), C.byref(tables), self.num_envs, self.env_id_offset,
+                                          self.n_envs_global, dev_index, C.byref(h)))
+        self._h = h
+        del keep
+        self._dev_index = dev_index
+        self.obs_dim = self._L.ptg_obs_dim(self._h)
+        self.obs_elems = int(self._L.ptg_obs_elems(self._h))
+        keys = (_abi.PtgObsKey * 16)()
+        nk = self._L.ptg_obs_layout(self._h, keys, 16)
+        self.obs_keys = [(keys[q].name.decode(), int(keys[q].dim), bool(keys[q].is_int32), int(keys[q].offset))
+                         for q in range(nk)]
+
+        n, dev = self.num_envs, self.device
+        self._obs = torch.zeros(self.obs_elems, dtype=torch.float32, device=dev)
+        self._term_obs = torch.zeros(self.obs_elems, dtype=torch.float32, device=dev)
+        self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._info = torch.zeros((_abi.PTG_N_INFO, n), dtype=torch.float64, device=dev)
+        self._ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
+        self._ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._io = self._make_io(self._obs, self._reward, self._done, self._term_obs,
+                                 self._info if self.cfg.train_or_eval else None, self._ep_ret, self._ep_len)
+        # pinned host mirrors for the numpy API
+        self._obs_h = torch.zeros(self.obs_elems, dtype=torch.float32).pin_memory()
+        self._term_obs_h = torch.zeros(self.obs_elems, dtype=torch.float32).pin_memory()
+        self._reward_h = torch.zeros(n, dtype=torch.float32).pin_memory()
+        self._done_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        self._info_h = torch.zeros((_abi.PTG_N_INFO, n), dtype=torch.float64).pin_memory()
+        self._ep_ret_h = torch.zeros(n, dtype=torch.float64).pin_memory()
+        self._ep_len_h = torch.zeros(n, dtype=torch.int32).pin_memory()
+        act_dtype = torch.float32 if self.action_type == "continuous" else torch.int64
+        self._act_h = torch.zeros(n, dtype=act_dtype).pin_memory()
+        self._act_d = torch.zeros(n, dtype=act_dtype, device=dev)
+        self._tape = None
+        self._t_start = time.time()
+        self._empty_infos = [{} for _ in range(n)]
+        self.bytes_per_env_step = int(self._L.ptg_bytes_per_env_step(self._h, _TORCH_ACT[act_dtype]))
+        if seed is not None:
+            self.seed(seed)
+
+    # ------------------------------------------------------------------------------------------------------
+    # plumbing
+    # ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _make_io(self, obs, reward, done, term_obs=None, info=None, ep_ret=None, ep_len=None) -> _abi.PtgIO:
+        io = _abi.PtgIO()
+        io.obs, io.reward, io.done = obs.data_ptr(), (reward.data_ptr() if reward is not None else None), (
+            done.data_ptr() if done is not None else None)
+        io.terminal_obs = term_obs.data_ptr() if term_obs is not None else None
+        io.info = info.data_ptr() if info is not None else None
+        io.episode_return = ep_ret.data_ptr() if ep_ret is not None else None
+        io.episode_length = ep_len.data_ptr() if ep_len is not None else None
+        return io
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _obs_views(self, buf: torch.Tensor) -> dict:
+        """dict key -> [n_envs, dim] view of one obs buffer (torch tensor on any device)."""
+        n, out = self.num_envs, {}
+        for name, dim, is_int, off in self.obs_keys:
+            v = buf[off:off + n * dim]
+            out[name] = v.view(torch.int32) if is_int else v.view(n, dim)
+        return out
+
+    def _obs_numpy(self, buf_h: torch.Tensor, rows=None) -> dict:
+        views = self._obs_views(buf_h)
+        out = {}
+        for name, dim, is_int, _ in self.obs_keys:
+            a = views[name].numpy()
+            if rows is not None:
+                a = a[rows]
+            out[name] = a.astype(np.int64) if is_int else a.astype(self.obs_dtype, copy=True)
+        return out
+
+    def _check_open(self):
+        if self._h is None:
+            raise RuntimeError("PtGVecEnv is closed")
+
+    def poll_error(self):
+        """Raise if the device saw an invalid action / ran past the market tables / exhausted the noise tape."""
+        _lib.check(self._L.ptg_poll_error(self._h, self._stream()))
+
+    # ------------------------------------------------------------------------------------------------------
+    # SB3 VecEnv interface (numpy)
+    # ------------------------------------------------------------------------------------------------------
+    def seed(self, seed: int | None = None) -> Sequence[int | None]:
+        """SB3: env i is re-seeded with ``seed + i`` at the next ``reset()`` (global env id for sharded envs)."""
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        self._seeds = [seed + self.env_id_offset + i for i in range(self.num_envs)]
+        return list(self._seeds)
+
+    def reset(self):
+        obs = self.reset_tensor(_return_views=False)
+        self._obs_h.copy_(self._obs, non_blocking=True)
+        want_info = self.num_envs <= self.info_limit
+        if want_info:
+            self._info_h.copy_(self._info, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.poll_error()
+        self.reset_infos = self._info_dicts(range(self.num_envs)) if want_info else [{} for _ in range(self.num_envs)]
+        del obs
+        return self._obs_numpy(self._obs_h)
+
+    def step_async(self, actions) -> None:
+        self._check_open()
+        a = np.asarray(actions)
+        if self.action_type == "continuous":
+            a = a.astype(np.float32, copy=False).reshape(self.num_envs)
+        else:
+            a = a.astype(np.int64, copy=False).reshape(self.num_envs)
+        self._act_h.numpy()[:] = a
+        self._act_d.copy_(self._act_h, non_blocking=True)
+        _lib.check(self._L.ptg_step(self._h, self._ptr(self._act_d), _TORCH_ACT[self._act_d.dtype],
+                                    C.byref(self._io), self._stream()))
+
+    def step_wait(self):
+        self._obs_h.copy_(self._obs, non_blocking=True)
+        self._reward_h.copy_(self._reward, non_blocking=True)
+        self._done_h.copy_(self._done, non_blocking=True)
+        eval_mode = bool(self.cfg.train_or_eval)
+        if eval_mode:
+            self._info_h.copy_(self._info, non_blocking=True)
+        stream = torch.cuda.current_stream(self.device)
+        stream.synchronize()
+        self.poll_error()
+        dones = self._done_h.numpy().astype(bool)
+        infos = self._info_dicts(range(self.num_envs)) if eval_mode else list(self._empty_infos)
+        if dones.any():
+            self._term_obs_h.copy_(self._term_obs, non_blocking=True)
+            self._ep_ret_h.copy_(self._ep_ret, non_blocking=True)
+            self._ep_len_h.copy_(self._ep_len, non_blocking=True)
+            stream.synchronize()
+            idx = np.nonzero(dones)[0]
+            term = self._obs_numpy(self._term_obs_h, rows=idx)
+            t_now = round(time.time() - self._t_start, 6)
+            ret, length = self._ep_ret_h.numpy(), self._ep_len_h.numpy()
+            for q, e in enumerate(idx):
+                d = dict(infos[e])
+                d["episode"] = {"r": round(float(ret[e]), 6), "l": int(length[e]), "t": t_now}   # Monitor
+                d["TimeLimit.truncated"] = False                     # the env only ever terminates (:478-481)
+                d["terminal_observation"] = {k: v[q] for k, v in term.items()}
+                infos[e] = d
+        return self._obs_numpy(self._obs_h), self._reward_h.numpy().copy(), dones, infos
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            self._L.ptg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _info_dicts(self, indices):
+        """24-field dicts in the reference's key order (ptg_gym_env.py:253-278) from the host info mirror."""
+        arr = self._info_h.numpy()
+        out = []
+        for e in indices:
+            col = arr[:, e]
+            d = {}
+            for f, key in enumerate(_abi.INFO_KEYS):
+                if key in ("step", "Meth_State", "Meth_Hot_Cold"):
+                    d[key] = int(col[f])
+                elif key == "Meth_Action":
+                    d[key] = _abi.STATE_NAMES[int(col[f])]
+                else:
+                    d[key] = float(col[f])
+            out.append(d)
+        return out
+
+    _STATE_ATTRS = {"Meth_State": "meth_state", "i": "i", "j": "j", "k": "k", "hot_cold": "hot_cold",
+                    "Meth_T_cat": "t_cat", "act_ep_h": "act_ep_h", "act_ep_d": "act_ep_d", "cum_rew": "cum_reward"}
+
+    def get_attr(self, attr_name: str, indices=None) -> list[Any]:
+        idx = list(self._get_indices(indices))
+        if attr_name in self._STATE_ATTRS:
+            col = self.get_state()[self._STATE_ATTRS[attr_name]]
+            return [col[i].item() for i in idx]
+        if attr_name == "current_action":
+            col = self.get_state()["current_action"]
+            return [_abi.STATE_NAMES[int(col[i])] for i in idx]
+        if hasattr(self, attr_name):
+            return [getattr(self, attr_name) for _ in idx]
+        raise AttributeError(attr_name)
+
+    def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
+        if attr_name in ("render_mode", "info_limit"):
+            setattr(self, attr_name, value)
+            return
+        raise AttributeError(f"attribute {attr_name!r} of the batched env cannot be set after construction")
+
+    def env_method(self, method_name: str, *method_args, indices=None, **method_kwargs) -> list[Any]:
+        raise NotImplementedError("the batched env has no per-env Python objects; use the VecEnv methods")
+
+    def env_is_wrapped(self, wrapper_class, indices=None) -> list[bool]:
+        """Monitor statistics are built in (infos[i]['episode']), so evaluate_policy may rely on them."""
+        is_monitor = getattr(wrapper_class, "__name__", "") == "Monitor"
+        return [is_monitor for _ in self._get_indices(indices)]
+
+    def get_images(self):
+        return [None for _ in range(self.num_envs)]
+
+    def render(self, mode: str | None = None):
+        return None
+
+    # ------------------------------------------------------------------------------------------------------
+    # device API (zero host copies)
+    # ------------------------------------------------------------------------------------------------------
+    def reset_tensor(self, seeds=None, mask=None, _return_views: bool = True):
+        """Reset (all or the masked) envs; returns dict of CUDA tensor views into the env's obs buffer."""
+        self._check_open()
+        if seeds is None and any(s is not None for s in self._seeds):
+            seeds = np.array([-1 if s is None else s for s in self._seeds], dtype=np.int64)
+        seeds_p = None
+        if seeds is not None:
+            seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+            assert seeds.shape == (self.num_envs,)
+            seeds_p = seeds.ctypes.data
+        mask_p = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            assert mask.shape == (self.num_envs,)
+            mask_p = mask.ctypes.data
+        io = self._make_io(self._obs, None, None, None, self._info)
+        _lib.check(self._L.ptg_reset(self._h, seeds_p, mask_p, C.byref(io), self._stream()))
+        self._reset_seeds()
+        return self._obs_views(self._obs) if _return_views else None
+
+    def step_tensor(self, actions: torch.Tensor):
+        """One step on device: ``actions`` is a CUDA tensor [n_envs] (int64/int32/uint8, or float32 for
+        continuous).  Returns (obs views, reward float32[n], done uint8[n]); buffers are reused every call."""
+        self._check_open()
+        a = actions.reshape(-1)
+        if a.device != self.device or a.numel() != self.num_envs or not a.is_contiguous():
+            raise ValueError("actions must be a contiguous CUDA tensor with n_envs elements on the env's device")
+        _lib.check(self._L.ptg_step(self._h, self._ptr(a), _TORCH_ACT[a.dtype], C.byref(self._io), self._stream()))
+        return self._obs_views(self._obs), self._reward, self._done
+
+    def rollout_tensor(self, actions: torch.Tensor, out: dict | None = None):
+        """T steps in ONE launch (state stays in registers): ``actions`` is [T, n_envs] on device.  Returns a dict
+        with ``obs`` [T, obs_elems] fp32 (key-major per step, see ``obs_views_of``), ``reward`` [T, n], ``done``
+        [T, n]; pass ``out`` to reuse buffers."""
+        self._check_open()
+        T = int(actions.shape[0])
+        if actions.device != self.device or actions.numel() != T * self.num_envs or not actions.is_contiguous():
+            raise ValueError("actions must be a contiguous CUDA tensor [T, n_envs] on the env's device")
+        if out is None:
+            out = {"obs": torch.empty((T, self.obs_elems), dtype=torch.float32, device=self.device),
+                   "reward": torch.empty((T, self.num_envs), dtype=torch.float32, device=self.device),
+                   "done": torch.empty((T, self.num_envs), dtype=torch.uint8, device=self.device)}
+        io = self._make_io(out["obs"], out["reward"], out["done"])
+        _lib.check(self._L.ptg_step_many(self._h, self._ptr(actions), _TORCH_ACT[actions.dtype], T, C.byref(io),
+                                         self._stream()))
+        return out
+
+    def obs_views_of(self, buf: torch.Tensor) -> dict:
+        """Key views of any single obs buffer with this env's layout (e.g. ``rollout['obs'][t]``)."""
+        return self._obs_views(buf)
+
+    @property
+    def terminal_obs_tensor(self) -> dict:
+        return self._obs_views(self._term_obs)
+
+    def set_noise_tape(self, tape) -> None:
+        """Tape-mode noise: [n_envs, L] fp64 values of ``normal(0, noise)`` consumed in order per env."""
+        t = torch.as_tensor(np.ascontiguousarray(tape, dtype=np.float64)).to(self.device)
+        assert t.shape[0] == self.num_envs
+        self._tape = t
+        _lib.check(self._L.ptg_set_noise_tape(self._h, self._ptr(t), t.shape[1]))
+
+    # ------------------------------------------------------------------------------------------------------
+    # state snapshot / statistics
+    # ------------------------------------------------------------------------------------------------------
+    def get_state(self) -> dict:
+        self._check_open()
+        s, arrays = _abi.alloc_state(self.num_envs)
+        _lib.check(self._L.ptg_get_state(self._h, C.byref(s)))
+        return arrays
+
+    def set_state(self, arrays: dict) -> None:
+        self._check_open()
+        s = _abi.PtgStateSoA()
+        keep = {}
+        for name, dt in _abi.STATE_FIELDS:
+            keep[name] = np.ascontiguousarray(arrays[name], dtype=dt)
+            assert keep[name].shape == (self.num_envs,)
+            setattr(s, name, keep[name].ctypes.data)
+        _lib.check(self._L.ptg_set_state(self._h, C.byref(s)))
+
+    def kernel_launches(self) -> int:
+        v = C.c_int64()
+        _lib.check(self._L.ptg_kernel_launches(self._h, C.byref(v)))
+        return int(v.value)
+
+    def episode_stats(self, clear: bool = True, reduce: bool = True) -> dict:
+        """Finished-episode statistics since the last clear: device reduction (warp shuffles, deterministic),
+        then -- if torch.distributed is initialised and ``reduce`` -- ONE all-gather of the 64-byte record over
+        NCCL/NVLink (gloo on CPU tests) and a fixed-order combine."""
+        self._check_open()
+        _lib.check(self._L.ptg_episode_stats(self._h, self._ptr(self._stats), int(clear), self._stream()))
+        return combine_stats(self._stats, reduce)
+
+
+def combine_stats(stats: torch.Tensor, reduce: bool = True) -> dict:
+    """All-gather one rank's 8 x fp64 ``PtgEpisodeStats`` record and combine in rank order."""
+    import torch.distributed as dist
+    if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        gathered = [torch.empty_like(stats) for _ in range(dist.get_world_size())]
+        dist.all_gather(gathered, stats)
+        per_rank = torch.stack(gathered).cpu().numpy()
+    else:
+        per_rank = stats.detach().cpu().numpy()[None, :]
+    L = _lib.load()
+    arr = (_abi.PtgEpisodeStats * per_rank.shape[0])()
+    for r in range(per_rank.shape[0]):
+        for f, (name, _) in enumerate(_abi.PtgEpisodeStats._fields_):
+            setattr(arr[r], name, float(per_rank[r, f]))
+    out = _abi.PtgEpisodeStats()
+    L.ptg_stats_combine(arr, per_rank.shape[0], C.byref(out))
+    n = out.count
+    mean = out.sum_return / n if n > 0 else float("nan")
+    var = max(out.sum_return_sq / n - mean * mean, 0.0) if n > 0 else float("nan")
+    return {"episodes": int(n), "return_mean": mean, "return_std": var ** 0.5, "length_mean": out.sum_length / n if n > 0
+            else float("nan"), "return_min": out.min_return, "return_max": out.max_return,
+            "env_steps": int(out.total_steps), "ranks": int(per_rank.shape[0])}
