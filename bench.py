@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched PtG environment on N B200s, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[3]'s environment -- BS2/OP2, "mod" observation design,
+discrete actions, training episodes -- with 1,048,576 envs PER GPU (weak scaling: each rank owns its own shard of
+the global env-id range, no data-path collective) on synthetic market/process data of the repo's shapes.
+One "step" = one VecEnv step over every env (one k_step launch per rank).
+
+  value     env-steps/s with the action tensor already resident in HBM (device API `step_tensor`)
+  e2e       the same through the SB3-style numpy API `env.step(actions)`: pinned H2D of the actions and D2H of
+            observations, rewards and dones inside the timed region
+  roofline  algorithmic HBM bytes per env-step (ptg_bytes_per_env_step) x envs / kernel time (CUDA
+            events around the timed region on the launching stream) vs the measured copy peak
+  cpu_baseline  the CPU oracle (a literal C restatement of the reference PTGEnv) on all host cores, bounded sample
+
+`--impl reference` times that CPU oracle as the reference arm (the reference itself is Python and cannot travel
+to the GPU box; tests/ pin the oracle bit-exactly to it).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 1 << 20
+WORKLOAD = "BS2/OP2 mod, discrete int64 actions, train episodes, synthetic data of repo shapes"
+METRIC, UNIT = "env-steps/sec", "env-steps/s"
+
+
+def make_kwargs(scenario=2, operation="OP2"):
+    import rl_ptg_b200 as ptg
+    E = ptg.EnvConfiguration(scenario=scenario, operation=operation)
+    price, op = ptg.synthetic_data(E, seed=0)
+    pp = ptg.Preprocessing(price, op, ptg.AgentConfiguration(), E, ptg.TrainConfiguration())
+    return pp.dict_env_kwargs("train")
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[q] for r in self.rows if len(r) >= 6 for q in range(4) if r[2 + q] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_rate(kw, n_envs: int, lock_steps: int, threads: int, warm: int = 5):
+    """env-steps/s of the CPU oracle (C restatement of PTGEnv, pthreads over envs) on this host."""
+    from oracle.ptg_oracle import OracleVecEnv, draw_noise_tape
+    tape = draw_noise_tape(3654 + np.arange(n_envs), kw["noise"], lock_steps + warm + 1)
+    env = OracleVecEnv(kw, n_envs, noise_tape=tape, threads=threads)
+    env.reset()
+    rng = np.random.default_rng(0)
+    acts = rng.integers(0, 5, size=(lock_steps + warm, n_envs))
+    for t in range(warm):
+        env.step(acts[t])
+    t0 = time.perf_counter()
+    for t in range(warm, warm + lock_steps):
+        env.step(acts[t])
+    dt = time.perf_counter() - t0
+    env.close()
+    return n_envs * lock_steps / dt, dt
+
+
+def run_reference(args):
+    """Reference arm: the CPU implementation of the path on the host cores (oracle port; see module docstring)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    kw = make_kwargs()
+    n_envs = 4096 * max(1, cores // 4)
+    # each "step" = one lock-step of the bounded sample; keep the whole run within a few minutes
+    rate, dt = cpu_oracle_rate(kw, n_envs, max(1, args.steps), cores, warm=max(1, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs": n_envs, "sample": f"{n_envs} envs x {args.steps} lock-steps"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_envs} envs x {args.steps} lock-steps, uniform random actions, tape noise"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from rl_ptg_b200.vec_env import PtGVecEnv, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_local = args.envs_per_gpu
+    n_global = n_local * world
+    lo, hi = shard_range(n_global, rank, world)
+    kw = make_kwargs()
+    env = PtGVecEnv(kw, hi - lo, seed=3654, device=dev, env_id_offset=lo, n_envs_global=n_global)
+    env.reset_tensor()
+    K, W = args.steps, args.warmup
+    n_pool = 8
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    pool = torch.randint(0, 5, (n_pool, n_local), generator=g, device=dev, dtype=torch.int64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value, roofline) ----------------
+    for t in range(W):
+        env.step_tensor(pool[t % n_pool])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = env.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for t in range(K):
+        env.step_tensor(pool[t % n_pool])
+    ev1.record()
+    barrier()
+    launches = env.kernel_launches() - l0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    env.poll_error()
+    stats = env.episode_stats(clear=True)       # the path's only collective: one 64-byte all-gather per roll-out
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+
+    # ---------------- rollout kernel (T steps per launch), reported in config ----------------
+    T = 16
+    acts_T = pool[:min(T, n_pool)].repeat((T + n_pool - 1) // n_pool, 1)[:T].contiguous()
+    out = None
+    roll_ms = None
+    if args.rollout:
+        out = env.rollout_tensor(acts_T)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = max(1, K // T)
+        for _ in range(reps):
+            env.rollout_tensor(acts_T, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        roll_ms = e0.elapsed_time(e1) / (reps * T)
+        del out
+
+    # ---------------- end to end through the numpy API ----------------
+    acts_h = [pool[q].cpu().numpy() for q in range(n_pool)]
+    Ke = max(3, min(K, args.e2e_steps))
+    for t in range(3):
+        env.step(acts_h[t % n_pool])
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(Ke):
+        obs, rew, done, infos = env.step(acts_h[t % n_pool])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e.item())
+    h2d = n_local * 8
+    d2h = env.obs_elems * 4 + n_local * 4 + n_local
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        bpe = env.bytes_per_env_step
+        kernel_ms = ms / K                                   # rank 0's own kernel time (CUDA events, same stream)
+        achieved = bpe * n_local / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(tp):
+            with open(tp) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+        cores = len(os.sched_getaffinity(0))
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            n_cpu = 4096 * max(1, cores // 4)
+            probe, _ = cpu_oracle_rate(kw, n_cpu, 10, cores, warm=2)                  # size the sample to ~15 s
+            args.cpu_lock_steps = int(min(2000, max(20, args.cpu_seconds * probe / n_cpu)))
+            rate, dt = cpu_oracle_rate(kw, n_cpu, args.cpu_lock_steps, cores)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"CPU oracle (C restatement of PTGEnv, pthreads), {n_cpu} envs x {args.cpu_lock_steps} "
+                             f"lock-steps = {dt:.1f} s"}
+        line = {
+            "metric": METRIC, "value": n_global * K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n_local, "envs_total": n_global,
+                       "obs_dim": env.obs_dim, "bytes_per_env_step": bpe, "noise": "on-device PCG64+ziggurat (numpy-exact)",
+                       "l2": f"per-step traffic {bpe * n_local / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
+                       "rollout_kernel_ms_per_step": roll_ms, "episodes_finished": stats["episodes"]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_step<4,true>",
+                         "kernel_ms": kernel_ms},
+            "cpu_baseline": cpu,
+            "e2e": {"value": n_global * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": Ke},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--cpu-lock-steps", type=int, default=150)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rollout", action="store_true", default=True)
+    ap.add_argument("--no-rollout", dest="rollout", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,7 +7,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "libptg_b200.so")
+SO_PATH = os.environ.get("PTG_B200_SO") or os.path.join(_HERE, "csrc", "libptg_b200.so")   # override: kernel experiments
 _LIB = None
 
 # every symbol include/ptg_b200.h declares

@@ -71,7 +71,11 @@ namespace {
 
 template <int NV, bool MOD>
 void launch_step_t(PtgHandle* h, const void* actions, int adtype, const PtgIO& io, int T, cudaStream_t st) {
-    k_step<NV, MOD><<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, T);
+    const unsigned grid = blocks_for(h->P.n_envs, PTG_BLOCK);
+    h->P.action_bytes = adtype == PTG_ACT_I64 ? 8 : adtype == PTG_ACT_U8 ? 1 : 4;
+    if (T > 0) k_step<NV, MOD, true, false><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, T);
+    else if (h->P.eval_mode && io.info) k_step<NV, MOD, false, true><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, 1);
+    else k_step<NV, MOD, false, false><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, 1);
 }
 template <int NV, bool MOD>
 void launch_reset_t(PtgHandle* h, const int64_t* seeds, const uint8_t* mask, const PtgIO& io, cudaStream_t st) {
@@ -164,7 +168,7 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     P.n_hours = (int32_t)tables->n_hours; P.n_days = (int32_t)tables->n_days;
     P.n_eps_ind = (int32_t)tables->n_eps_ind;
     P.continuous = c.action_type; P.eval_mode = c.train_or_eval; P.noise_mode = c.noise_mode;
-    P.schedule_mode = c.schedule_mode; P.b_s3 = c.scenario == 3 ? 1 : 0;     // :76-77
+    P.schedule_mode = c.schedule_mode;
     P.penalty = c.reward_level * c.state_change_penalty;                       // :332
     P.has_penalty = P.penalty != 0.0;
     P.time1_start_p_f = c.time1_start_p_f; P.time2_start_f_p = c.time2_start_f_p; P.time_p_f = c.time_p_f;
@@ -175,12 +179,15 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     P.time34_f_p_f = c.time34_f_p_f; P.time4_f_p_f = c.time4_f_p_f; P.time45_f_p_f = c.time45_f_p_f;
     P.time5_f_p_f = c.time5_f_p_f; P.i_fully_developed = c.i_fully_developed; P.j_fully_developed = c.j_fully_developed;
     P.noise = c.noise; P.eps_len_d = c.eps_len_d;
-    P.convert_mol_to_Nm3 = c.convert_mol_to_Nm3; P.H_u_CH4 = c.H_u_CH4; P.H_u_H2 = c.H_u_H2; P.dt_water = c.dt_water;
-    P.cp_water = c.cp_water; P.rho_water = c.rho_water; P.Molar_mass_CO2 = c.Molar_mass_CO2;
-    P.Molar_mass_H2O = c.Molar_mass_H2O; P.h_H2O_evap = c.h_H2O_evap; P.eeg_el_price = c.eeg_el_price;
-    P.heat_price = c.heat_price; P.o2_price = c.o2_price; P.water_price = c.water_price;
-    P.min_load_electrolyzer = c.min_load_electrolyzer; P.max_h2_volumeflow = c.max_h2_volumeflow; P.eta_CHP = c.eta_CHP;
-    P.sim_step_d = (double)c.sim_step;
+    RewardConsts& R = P.rc;
+    R.convert_mol_to_Nm3 = c.convert_mol_to_Nm3; R.H_u_CH4 = c.H_u_CH4; R.H_u_H2 = c.H_u_H2; R.dt_water = c.dt_water;
+    R.cp_water = c.cp_water; R.rho_water = c.rho_water; R.Molar_mass_CO2 = c.Molar_mass_CO2;
+    R.Molar_mass_H2O = c.Molar_mass_H2O; R.h_H2O_evap = c.h_H2O_evap; R.eeg_el_price = c.eeg_el_price;
+    R.heat_price = c.heat_price; R.o2_price = c.o2_price; R.water_price = c.water_price;
+    R.min_load_electrolyzer = c.min_load_electrolyzer; R.max_h2_volumeflow = c.max_h2_volumeflow; R.eta_CHP = c.eta_CHP;
+    R.sim_step_d = (double)c.sim_step; R.penalty = P.penalty;
+    R.b_s3 = c.scenario == 3 ? 1 : 0;                                          // :76-77
+    B.rc = R;
     for (int q = 0; q < 6; ++q) P.prob_thre[q] = -1 + q * ((1.0 - (-1.0)) / 5);   // :151-155
 
     // ---- observation layout: key-major blocks, each block start 16 B aligned ----
@@ -234,13 +241,15 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
 
     // ---- build the device tables ----
     StepEntry* step_tab = nullptr;
+    StepMeans* mean_tab = nullptr;
     PTG_TRY(h->alloc(&step_tab, (size_t)ent));
-    k_build_step_tab<<<blocks_for(ent, 128), 128>>>(B, step_tab);
+    PTG_TRY(h->alloc(&mean_tab, (size_t)ent));
+    k_build_step_tab<<<blocks_for(ent, 128), 128>>>(B, step_tab, mean_tab);
     int32_t* lut = nullptr;
     PTG_TRY(h->alloc(&lut, (size_t)B.n_vals * PTG_N_ARGMIN));
     k_build_argmin<<<dim3((unsigned)B.n_vals, PTG_N_ARGMIN), 256>>>(B, lut);
     h->launches += 2;
-    P.step_tab = step_tab; P.argmin_lut = lut;
+    P.step_tab = step_tab; P.mean_tab = mean_tab; P.argmin_lut = lut;
 
     PTG_TRY(h->alloc(&h->d_err, 1));
     PTG_TRY(cudaMemset(h->d_err, 0, sizeof(uint32_t)));
@@ -316,6 +325,11 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     PTG_TRY(h->alloc(&h->d_partial, PTG_STATS_BLOCKS));
     PTG_TRY(h->alloc(&h->d_state_i32, n * 13)); PTG_TRY(h->alloc(&h->d_state_i64, n)); PTG_TRY(h->alloc(&h->d_state_f64, n * 2));
     P.tape = nullptr; P.tape_len = 0;
+    {   // one scheduling wave = resident CTAs of the step kernel on this device
+        cudaDeviceProp prop{};
+        PTG_TRY(cudaGetDeviceProperties(&prop, device));
+        P.prefetch_distance = prop.multiProcessorCount * PTG_STEP_MIN_BLOCKS * PTG_BLOCK;
+    }
     k_construct<<<blocks_for(n_envs, 256), 256>>>(P);
     h->launches += 1;
     PTG_TRY(cudaDeviceSynchronize());
@@ -370,7 +384,7 @@ extern "C" int ptg_step(PtgHandle* h, const void* actions, int action_dtype, con
     int rc = check_step_io(h, actions, action_dtype, io);
     if (rc != PTG_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PTG_DISPATCH(launch_step_t, h, actions, action_dtype, *io, 1, st);
+    PTG_DISPATCH(launch_step_t, h, actions, action_dtype, *io, 0, st);
     h->launches += 1;
     h->total_steps += (double)h->P.n_envs;
     PTG_CUDA(cudaGetLastError());

@@ -14,15 +14,25 @@
 #define PTG_BLOCK 256            // threads per CTA of the step kernels
 #define PTG_N_ARGMIN 6           // argmin targets: cooldown, standby_up, standby_down, startup_cold, startup_hot, op1
 
-// --- step table entry: 80 B, 16 B aligned -----------------------------------------------------------------
+// --- step table entry: 64 B, 64 B aligned (exactly two 32 B sectors per gather) ---------------------------
+// The reward of :280-334 is linear in the three prices once the window means are fixed:
+//     rew = c_gas * gas + c_eua * eua - c_el * el + c_0            (already scaled by sim_step / 3600)
+// so the table-build kernel evaluates the flow-dependent factors -- including the PEM electrolyzer efficiency
+// basis functions (:312-317) and the CHP/EEG terms (:291-297) -- once per (table, start row) and the step
+// kernel is left with three fp64 FMAs.
 struct __align__(16) StepEntry {
-    double mean[5];     // window means: H2, CH4, H2_res, H2O, P_el (fp64, numpy pairwise order)
-    double t_end;       // T_cat after the step (last row of the window)
+    double c_gas, c_eua, c_el, c_0;
     float norm[6];      // min-max normalised T_cat, H2, CH4, H2_res, H2O, P_el -- fp32(fp64 expression of :212-217)
     int32_t tinfo;      // (T value id << 3) | flags(T_end)
     int32_t _pad;
 };
-static_assert(sizeof(StepEntry) == 80, "StepEntry layout");
+static_assert(sizeof(StepEntry) == 64, "StepEntry layout");
+
+// --- window statistics in fp64, only read for the eval-mode info dict (:251-278) -------------------------
+struct __align__(16) StepMeans {
+    double mean[5];     // window means: H2, CH4, H2_res, H2O, P_el (fp64, numpy pairwise order)
+    double t_end;       // T_cat after the step (last row of the window)
+};
 
 #define PTG_TF_COLD 1       // T <= t_cat_startup_cold   (:339)
 #define PTG_TF_HOT 2        // T >= t_cat_startup_hot    (:341)
@@ -57,6 +67,14 @@ PTG_HD uint32_t meta_pack(const Meta& r) {
            ((uint32_t)r.part_ds << 6) | ((uint32_t)r.full_ds << 11) | ((uint32_t)r.cur_action << 16);
 }
 
+// Scalars of the reward model, shared by the table-build kernel and the eval-mode info path.
+struct RewardConsts {
+    double convert_mol_to_Nm3, H_u_CH4, H_u_H2, dt_water, cp_water, rho_water, Molar_mass_CO2, Molar_mass_H2O,
+           h_H2O_evap, eeg_el_price, heat_price, o2_price, water_price, min_load_electrolyzer, max_h2_volumeflow,
+           eta_CHP, sim_step_d, penalty;
+    int32_t b_s3, _pad;
+};
+
 // --- everything a kernel needs, passed by value (__grid_constant__) ---------------------------------------------
 struct DevParams {
     // sizes
@@ -68,10 +86,13 @@ struct DevParams {
     int32_t eps_sim_steps, sim_step;
     int32_t n_hours, n_days, n_vals, n_eps_ind;
     int32_t raw;               // 1 = raw observation design
-    int32_t continuous, eval_mode, noise_mode, schedule_mode, b_s3;
+    int32_t continuous, eval_mode, noise_mode, schedule_mode;
     int32_t has_penalty;
+    int32_t prefetch_distance;     // envs between a CTA and the CTA whose state it prefetches into L2
+    int32_t action_bytes;          // element size of the action tensor of the current launch
     // tables (device)
     const StepEntry* step_tab;
+    const StepMeans* mean_tab;     // same indexing as step_tab
     const int32_t* argmin_lut;     // [n_vals][6]
     const float4* hour_tab;        // [n_hours][nv]
     const DayRow* day_tab;         // [n_days]
@@ -94,9 +115,7 @@ struct DevParams {
     int32_t i_fully_developed, j_fully_developed;
     // scalars
     double noise, eps_len_d, penalty /* r_0 * state_change_penalty */;
-    double convert_mol_to_Nm3, H_u_CH4, H_u_H2, dt_water, cp_water, rho_water, Molar_mass_CO2, Molar_mass_H2O,
-           h_H2O_evap, eeg_el_price, heat_price, o2_price, water_price, min_load_electrolyzer, max_h2_volumeflow,
-           eta_CHP, sim_step_d;
+    RewardConsts rc;
     double prob_thre[6];           // continuous-action thresholds, :151-155
     // obs block offsets (elements) inside the obs buffer, see ptg_obs_layout
     int64_t off_win0, off_win1;    // mod: Pot_Reward, Part_Full | raw: Elec_Price, (unused)
@@ -155,8 +174,10 @@ __device__ __forceinline__ int cur_table(const Meta& m) {
     }
 }
 
-// One draw of np_random.normal(0, noise, size=1)[0]
-__device__ __forceinline__ double draw_noise(const DevParams& P, int64_t e) {
+// One draw of np_random.normal(0, noise, size=1)[0].  Out of line on purpose: only transitions into
+// standby/cooldown/startup draw, and the 128-bit PCG64 arithmetic would otherwise inflate the register
+// footprint of every thread of the step kernel.
+__device__ __noinline__ double draw_noise(const DevParams& P, int64_t e) {
     if (P.noise_mode == PTG_NOISE_OFF) return 0.0;
     int64_t d = P.draws[e];
     P.draws[e] = d + 1;
@@ -179,7 +200,7 @@ __device__ __forceinline__ int jitter_index(int idx, double nz) {
 }
 
 // _get_reward, :280-334 -- same operation order as the reference, fp64, no fused multiply-add (-fmad=false)
-__device__ __forceinline__ void reward_parts(const DevParams& P, const double* mean, double el, double gas,
+__device__ __forceinline__ void reward_parts(const RewardConsts& P, const double* mean, double el, double gas,
                                              double eua, int state_change, RewardParts& r) {
     const double H2 = mean[0], CH4 = mean[1], H2res = mean[2], H2O = mean[3], heat = mean[4];
     double ch4_volumeflow = CH4 * P.convert_mol_to_Nm3;
@@ -214,6 +235,18 @@ __device__ __forceinline__ void reward_parts(const DevParams& P, const double* m
     r.rew = state_change ? r.rew_unpenalised - P.penalty : r.rew_unpenalised;
 }
 
+// The price-linear form of the reward above (see StepEntry): evaluated once per table entry by k_build_step_tab.
+__device__ __forceinline__ void reward_coefficients(const RewardConsts& P, const double* mean, double& c_gas,
+                                                    double& c_eua, double& c_el, double& c_0) {
+    RewardParts u;
+    reward_parts(P, mean, 1.0, 1.0, 1.0, 0, u);        // unit prices: each price-dependent term is its factor
+    const double scale = P.sim_step_d / 3600;
+    c_gas = u.ch4_rev * scale;
+    c_eua = u.eua_rev * scale;
+    c_el = (u.heat_cost + u.ely_cost) * scale;
+    c_0 = (u.chp_rev + u.steam_rev + u.o2_rev - u.water_cost) * scale;
+}
+
 // Decode the action of env e (discrete id, or continuous Box(-1,1) -> 5 bins, :346-355)
 __device__ __forceinline__ int decode_action(const DevParams& P, const void* actions, int dtype, int64_t idx,
                                              int prev_action) {
@@ -245,11 +278,24 @@ __device__ __forceinline__ void episode_offsets(const DevParams& P, int64_t e, i
     ep_d = (int)(v * P.eps_len_d);                // :61 / :492
 }
 
+// Which argmin-LUT column (if any) the coming transition will read: known as soon as (action, state, T flags) are,
+// so the LUT gather and the RNG-state prefetch can be issued before the branchy transition code runs.
+//   return: column 0..5, or -1 when no _get_index is evaluated;  draws = 1 when the transition draws noise
+__device__ __forceinline__ int argmin_column(int action, const Meta& m, int tflags, int& draws) {
+    const int hot = (tflags & PTG_TF_COLD) ? 0 : (tflags & PTG_TF_HOT) ? 1 : m.hot_cold;     // :339-342
+    draws = 0;
+    if (action == PTG_STANDBY && m.state != PTG_STANDBY) { draws = 1; return (tflags & PTG_TF_SBUP) ? 1 : 2; }
+    if (action == PTG_COOLDOWN && m.state != PTG_COOLDOWN) { draws = 1; return 0; }
+    if (action == PTG_STARTUP && m.state < PTG_STARTUP) { draws = 1; return hot ? 4 : 3; }
+    if (action == PTG_PARTIAL_LOAD && m.state == PTG_FULL_LOAD && m.full_ds == PTG_DS_OP2_START_F) return 5;
+    return -1;
+}
+
 // The plant transition of PTGEnv.step (:336-440 + _perform_sim_step) -> new (core, tinfo) and the step-table
-// entry index that holds this step's window statistics.
+// entry index that holds this step's window statistics.  `lut_val` = argmin_lut[vid][argmin_column(...)].
 __device__ __forceinline__ int plant_transition(const DevParams& P, int64_t e, int action, int& i, int& j, Meta& m,
-                                                int32_t tinfo_in) {
-    const int tflags = tinfo_in & 7, vid = tinfo_in >> 3;
+                                                int32_t tinfo_in, int lut_val) {
+    const int tflags = tinfo_in & 7;
     if (tflags & PTG_TF_COLD) m.hot_cold = 0;          // :339-342
     else if (tflags & PTG_TF_HOT) m.hot_cold = 1;
     m.cur_action = action;
@@ -269,30 +315,27 @@ __device__ __forceinline__ int plant_transition(const DevParams& P, int64_t e, i
         next_state = (state == PTG_STARTUP) ? PTG_PARTIAL_LOAD : state;
         change = (state == PTG_STARTUP);
     } else if (action <= PTG_STARTUP) {                 // _standby / _cooldown / _startup, :572-625
-        int col;
         if (action == PTG_STANDBY) {
             m.sb_up = (tflags & PTG_TF_SBUP) ? 1 : 0;
             ds = m.sb_up ? PTG_DS_STANDBY_UP : PTG_DS_STANDBY_DOWN;
-            col = m.sb_up ? 1 : 2;
             next_state = PTG_STANDBY;
         } else if (action == PTG_COOLDOWN) {
-            ds = PTG_DS_COOLDOWN; col = 0; next_state = PTG_COOLDOWN;
+            ds = PTG_DS_COOLDOWN; next_state = PTG_COOLDOWN;
         } else {
             m.part_ds = PTG_DS_OP1_START_P; m.full_ds = PTG_DS_OP2_START_F;
             m.su_hot = m.hot_cold;
             ds = m.su_hot ? PTG_DS_STARTUP_HOT : PTG_DS_STARTUP_COLD;
-            col = m.su_hot ? 4 : 3;
             next_state = PTG_PARTIAL_LOAD; change = 1;
         }
         state = action;
-        i = jitter_index(P.argmin_lut[vid * PTG_N_ARGMIN + col], draw_noise(P, e));
+        i = jitter_index(lut_val, draw_noise(P, e));
         j = 1;
     } else if (action == PTG_PARTIAL_LOAD) {            // _partial, :627-691
         state = PTG_PARTIAL_LOAD; next_state = PTG_PARTIAL_LOAD;
         const int time_op = i + j * S;
         int nds = PTG_DS_OP8_F_P, ni = 0, nj = 1;
         if (m.full_ds == PTG_DS_OP2_START_F) {
-            if (time_op < P.time2_start_f_p) { nds = PTG_DS_OP1_START_P; ni = P.argmin_lut[vid * PTG_N_ARGMIN + 5]; }
+            if (time_op < P.time2_start_f_p) { nds = PTG_DS_OP1_START_P; ni = lut_val; }
         } else if (m.full_ds == PTG_DS_OP3_P_F) {
             if (time_op < P.time1_p_f_p) { ni = P.i_fully_developed; nj = P.j_fully_developed; }
             else if (P.time1_p_f_p < time_op && time_op < P.time2_p_f_p) { nds = PTG_DS_OP4_P_F_P_5; ni = i; nj = j + 1; }

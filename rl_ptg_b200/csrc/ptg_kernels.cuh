@@ -29,6 +29,7 @@ struct BuildParams {
     int32_t n_vals;
     double t_cat_standby, t_cat_startup_cold, t_cat_startup_hot;
     double lo[6], hi[6];                  // normalisation bounds: T, h2, ch4, h2_res, h2o, heat
+    RewardConsts rc;
 };
 
 // Virtual S-row window of _perform_sim_step (env/ptg_gym_env.py:525-557) starting at row s of table ds:
@@ -83,7 +84,7 @@ __device__ __forceinline__ int tinfo_of(const BuildParams& B, double T) {
     return (find_val(B.vals, B.n_vals, T) << 3) | flags;
 }
 
-__global__ void k_build_step_tab(const __grid_constant__ BuildParams B, StepEntry* out) {
+__global__ void k_build_step_tab(const __grid_constant__ BuildParams B, StepEntry* out, StepMeans* out_means) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= B.n_entries) return;
     int ds = 0;
@@ -105,15 +106,18 @@ __global__ void k_build_step_tab(const __grid_constant__ BuildParams B, StepEntr
     }
     w.n = w.head_rows + ov;
     StepEntry e;
+    StepMeans sm;
 #pragma unroll
-    for (int c = 0; c < 5; ++c) e.mean[c] = window_pairwise_sum(w, 2 + c, 0, w.n) / (double)w.n;   // np.average
-    e.t_end = w.at(w.n - 1, 1);
-    e.norm[0] = (float)((e.t_end - B.lo[0]) / (B.hi[0] - B.lo[0]));
+    for (int c = 0; c < 5; ++c) sm.mean[c] = window_pairwise_sum(w, 2 + c, 0, w.n) / (double)w.n;   // np.average
+    sm.t_end = w.at(w.n - 1, 1);
+    e.norm[0] = (float)((sm.t_end - B.lo[0]) / (B.hi[0] - B.lo[0]));
 #pragma unroll
-    for (int c = 0; c < 5; ++c) e.norm[1 + c] = (float)((e.mean[c] - B.lo[1 + c]) / (B.hi[1 + c] - B.lo[1 + c]));
-    e.tinfo = tinfo_of(B, e.t_end);
+    for (int c = 0; c < 5; ++c) e.norm[1 + c] = (float)((sm.mean[c] - B.lo[1 + c]) / (B.hi[1 + c] - B.lo[1 + c]));
+    reward_coefficients(B.rc, sm.mean, e.c_gas, e.c_eua, e.c_el, e.c_0);
+    e.tinfo = tinfo_of(B, sm.t_end);
     e._pad = 0;
     out[g] = e;
+    out_means[g] = sm;
 }
 
 // argmin LUT: lut[v][c] = first index of min |T_c[:] - vals[v]|  (np.abs(..).argmin(), :521-522)
@@ -258,43 +262,33 @@ __device__ __forceinline__ void emit_obs(const DevParams& P, float* __restrict__
     sc[8 * P.n_pad] = o.cos_h;
 }
 
-// Snapshot of one env's observation inputs, built only inside the rare branches that call the noinline helpers
-// below (so the hot path keeps hrow/day/o in registers instead of addressable local memory).
-template <int NV>
-struct ObsSnap {
-    float4 hrow[NV];
-    DayRow day;
-    ObsRegs o;
+// Everything one env contributes to an observation can be re-derived from five integers: the step-table entry
+// (or -1 for the reset row), the market row indices, METH_STATUS and the clock index.  The cold paths below
+// (terminal observation, masked reset, eval-mode info) take those scalars and re-read the L2-resident tables, so
+// the hot path never has to keep addressable copies of its registers.
+struct ObsKey {
+    int ent, t_hour, t_day, status, k1;
 };
-template <int NV>
-__device__ __forceinline__ ObsSnap<NV> make_snap(const float4 (&hrow)[NV], const DayRow& day, const ObsRegs& o) {
-    ObsSnap<NV> s;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) s.hrow[v] = hrow[v];
-    s.day = day; s.o = o;
-    return s;
-}
 
-// Scalar (uncoalesced) emission of one env's observation -- terminal observations only (rare).
+// Scalar (uncoalesced) emission of one env's observation -- terminal observations and masked resets (rare).
 template <int NV, bool MOD>
-__device__ __noinline__ void emit_obs_scalar(const DevParams& P, float* __restrict__ obs, int64_t e,
-                                             const ObsSnap<NV> snap) {
-    const float* w = reinterpret_cast<const float*>(snap.hrow);
-    const DayRow& day = snap.day;
-    const ObsRegs& o = snap.o;
+__device__ __noinline__ void emit_obs_scalar(const DevParams& P, float* __restrict__ obs, int64_t e, ObsKey key) {
+    const float* w = reinterpret_cast<const float*>(P.hour_tab + (int64_t)key.t_hour * NV);
     for (int a = 0; a < P.pa; ++a) obs[P.off_win0 + e * P.pa + a] = w[a];
     if (MOD) {
         const uint32_t bits = __float_as_uint(w[4 * NV - 3]);
         for (int a = 0; a < P.pa; ++a) obs[P.off_win1 + e * P.pa + a] = (float)((bits >> (2 * a)) & 3u) - 1.0f;
     } else {
+        const DayRow day = P.day_tab[key.t_day];
         obs[P.off_gas + 2 * e] = day.gas_n0; obs[P.off_gas + 2 * e + 1] = day.gas_n1;
         obs[P.off_eua + 2 * e] = day.eua_n0; obs[P.off_eua + 2 * e + 1] = day.eua_n1;
     }
     float* sc = obs + P.off_scalar + e;
-    sc[0] = __int_as_float(o.status);
-    for (int q = 0; q < 6; ++q) sc[(1 + q) * P.n_pad] = o.norm[q];
-    sc[7 * P.n_pad] = o.sin_h;
-    sc[8 * P.n_pad] = o.cos_h;
+    sc[0] = __int_as_float(key.status);
+    for (int q = 0; q < 6; ++q) sc[(1 + q) * P.n_pad] = key.ent >= 0 ? P.step_tab[key.ent].norm[q] : P.reset_norm[q];
+    const ClockRow c = P.clock_tab[key.k1];
+    sc[7 * P.n_pad] = c.sin_h;
+    sc[8 * P.n_pad] = c.cos_h;
 }
 
 template <int NV>
@@ -327,33 +321,46 @@ __device__ __forceinline__ void clamp_market_index(const DevParams& P, int& t_ho
 }
 
 // _get_info, :251-278, feature-major fp64 [24][n_envs]
-struct InfoSnap {
-    int k, t_hour, state, cur_action, hot_cold;
-    double el, gas, eua, t_cat, flow[5], cum_rew;
-    RewardParts r;
+struct InfoKey {
+    int k, t_hour, t_day, ent, state_change;   // ent < 0: reset (no reward constituents yet)
+    uint32_t meta;
+    double rew, cum_rew;
 };
-__device__ __noinline__ void write_info(const DevParams& P, double* info, int64_t e, const InfoSnap s) {
+template <int NV>
+__device__ __noinline__ void write_info(const DevParams& P, double* info, int64_t e, InfoKey s) {
     const int64_t n = P.n_envs;
     double* f = info + e;
-    const int k = s.k, t_hour = s.t_hour;
-    const double t_cat = s.t_cat, cum_rew = s.cum_rew;
-    const double* flow = s.flow;
-    const RewardParts& r = s.r;
-    f[0 * n] = k;
-    f[1 * n] = s.el;
-    f[2 * n] = s.gas;
-    f[3 * n] = s.eua;
-    f[4 * n] = s.state;
-    f[5 * n] = s.cur_action;
-    f[6 * n] = s.hot_cold;
+    const Meta m = meta_unpack(s.meta);
+    const double el = *reinterpret_cast<const double*>(reinterpret_cast<const float*>(P.hour_tab + (int64_t)s.t_hour * NV) + 4 * NV - 2);
+    const DayRow day = P.day_tab[s.t_day];
+    double flow[5], t_cat;
+    RewardParts r = {};
+    if (s.ent >= 0) {          // constituents in the reference's operation order, from the fp64 window means
+        const StepMeans sm = P.mean_tab[s.ent];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) flow[q] = sm.mean[q];
+        t_cat = sm.t_end;
+        reward_parts(P.rc, flow, el, day.gas, day.eua, s.state_change, r);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) flow[q] = P.reset_flow[q];
+        t_cat = 16.0;
+    }
+    f[0 * n] = s.k;
+    f[1 * n] = el;
+    f[2 * n] = day.gas;
+    f[3 * n] = day.eua;
+    f[4 * n] = m.state;
+    f[5 * n] = m.cur_action;
+    f[6 * n] = m.hot_cold;
     f[7 * n] = t_cat;
     f[8 * n] = flow[0]; f[9 * n] = flow[1]; f[10 * n] = flow[3]; f[11 * n] = flow[4];
     f[12 * n] = r.ch4_rev; f[13 * n] = r.steam_rev; f[14 * n] = r.o2_rev; f[15 * n] = r.eua_rev; f[16 * n] = r.chp_rev;
     f[17 * n] = -r.heat_cost; f[18 * n] = -r.ely_cost; f[19 * n] = -r.water_cost;
-    f[20 * n] = r.rew;
-    f[21 * n] = cum_rew;
-    f[22 * n] = P.pot0[t_hour];
-    f[23 * n] = P.pf0[t_hour];
+    f[20 * n] = s.rew;         // "reward [ct]" is the value step() returned
+    f[21 * n] = s.cum_rew;
+    f[22 * n] = P.pot0[s.t_hour];
+    f[23 * n] = P.pf0[s.t_hour];
 }
 
 // _initialize_op_rew (:105-138) + episode offsets; returns the reset (core, tinfo, ep)
@@ -402,7 +409,7 @@ __global__ void k_construct(const __grid_constant__ DevParams P) {
 
 template <int NV, bool MOD>
 __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ DevParams P, const int64_t* seeds,
-                                                     const uint8_t* mask, PtgIO io) {
+                                                     const uint8_t* mask, const __grid_constant__ PtgIO io) {
     __shared__ __align__(16) float stage[PTG_BLOCK / 32][32 * 4 * NV];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -442,24 +449,146 @@ __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ Dev
     }
     if (io.obs != nullptr) {
         if (mask == nullptr) emit_obs<NV, MOD>(P, io.obs, stage[wid], e, active, lane, warp_env0, nvalid, hrow, day, o);
-        else if (doit) emit_obs_scalar<NV, MOD>(P, io.obs, e, make_snap<NV>(hrow, day, o));
+        else if (doit) emit_obs_scalar<NV, MOD>(P, io.obs, e, ObsKey{-1, t_hour, t_day, PTG_COOLDOWN, 0});
     }
     if (doit && io.info != nullptr) {
-        InfoSnap s = {};
-        s.k = 0; s.t_hour = t_hour; s.state = m.state; s.cur_action = m.cur_action; s.hot_cold = m.hot_cold;
-        s.el = hour_row_el<NV>(hrow); s.gas = day.gas; s.eua = day.eua; s.t_cat = 16.0; s.cum_rew = 0.0;
-#pragma unroll
-        for (int q = 0; q < 5; ++q) s.flow[q] = P.reset_flow[q];
-        write_info(P, io.info, e, s);
+        write_info<NV>(P, io.info, e, InfoKey{0, t_hour, t_day, -1, 0, meta_pack(m), 0.0, 0.0});
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // step
 // ------------------------------------------------------------------------------------------------------------
+// End of an episode (rare): record the terminal observation and the Monitor record, fold the episode into the
+// finished-episode accumulators and write the reset state (next entry of the episode schedule) to global memory.
 template <int NV, bool MOD>
-__global__ void __launch_bounds__(PTG_BLOCK) k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions,
-                                                    int adtype, PtgIO io, int T) {
+__device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io, int64_t e, bool record, int k,
+                                            double ep_ret, int cur_action, ObsKey key) {
+    if (record) {
+        if (io.terminal_obs != nullptr) emit_obs_scalar<NV, MOD>(P, io.terminal_obs, e, key);
+        if (io.episode_return != nullptr) io.episode_return[e] = ep_ret;
+        if (io.episode_length != nullptr) io.episode_length[e] = k;
+    }
+    P.fin_cnt[e] += 1;
+    P.fin_ret_sum[e] += ep_ret;
+    P.fin_ret_sq[e] += ep_ret * ep_ret;
+    P.fin_len_sum[e] += (double)k;
+    P.fin_min[e] = fmin(P.fin_min[e], ep_ret);
+    P.fin_max[e] = fmax(P.fin_max[e], ep_ret);
+    const int32_t mc = P.ep_count[e] + 1;
+    P.ep_count[e] = mc;
+    Meta m;
+    m.cur_action = cur_action;
+    int4 core; int32_t tinfo; int2 ep;
+    env_reset_state(P, e, mc, core, tinfo, ep, m);
+    P.core[e] = core; P.tinfo[e] = tinfo; P.ep[e] = ep; P.ep_ret[e] = 0.0;
+    if (P.has_penalty) P.nchg[e] = 0;
+}
+
+#ifndef PTG_STEP_MIN_BLOCKS
+#define PTG_STEP_MIN_BLOCKS 4        // CTAs of 256 threads per SM the step kernel is compiled for (<= 64 registers)
+#endif
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// One env step of one thread.  Register discipline: only the packed plant state is live across the (branchy,
+// possibly calling) plant transition; the market rows are *prefetched* into L1 before it and loaded after it.
+template <int NV, bool MOD, bool EVAL>
+__device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, const void* __restrict__ actions,
+                                         int adtype, int64_t act_idx, bool single, int64_t e, bool active, int lane,
+                                         int64_t warp_env0, int nvalid, float* sm, float* __restrict__ obs_out,
+                                         float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int& i, int& j,
+                                         int& k, uint32_t& meta, int32_t& tinfo, int2& ep, double& ep_ret) {
+    float4 hrow[NV];
+    DayRow day;
+    ObsRegs o;
+    float reward = 0.f;
+    int done = 0;
+    if (active) {
+        // (a) clock row of step k+1 -> market row indices of the NEW hour/day (:442-447); warm L1 with them
+        const int4 c4 = __ldg(reinterpret_cast<const int4*>(P.clock_tab + (k + 1)));
+        int t_hour = ep.x + c4.z, t_day = ep.y + c4.w;
+        clamp_market_index(P, t_hour, t_day);
+        {
+            const char* hp = reinterpret_cast<const char*>(P.hour_tab + (int64_t)t_hour * NV);
+#pragma unroll
+            for (int b = 0; b < NV * 16; b += 32) prefetch_l1(hp + b);
+            prefetch_l1(P.day_tab + t_day);
+        }
+        // (b) plant transition -> step-table entry.  The argmin-LUT gather and the RNG-state lines are requested
+        //     first, so their latency overlaps the clock/market prefetches above and the branchy code below.
+        Meta m = meta_unpack(meta);
+        const int action = decode_action(P, actions, adtype, act_idx, m.cur_action);
+        const int prev_state = m.state;
+        int will_draw;
+        const int col = argmin_column(action, m, tinfo & 7, will_draw);
+        int lut_val = 0;
+        if (col >= 0) lut_val = __ldg(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + col);
+        if (will_draw && P.noise_mode != PTG_NOISE_OFF) {
+            prefetch_l1(P.draws + e);
+            if (P.noise_mode == PTG_NOISE_NUMPY) { prefetch_l1(P.rng_state + e); prefetch_l1(P.rng_inc + e); }
+        }
+        const int ent = plant_transition(P, e, action, i, j, m, tinfo, lut_val);
+        meta = meta_pack(m);
+        const int state_change = (prev_state != m.state);
+        // (c) gathers: entry (4 x 16 B = two sectors), hour row, day row
+        const int4* ep4 = reinterpret_cast<const int4*>(P.step_tab + ent);
+        const int4 q0 = __ldg(ep4), q1 = __ldg(ep4 + 1), q2 = __ldg(ep4 + 2), q3 = __ldg(ep4 + 3);
+        load_hour_row<NV>(P, t_hour, hrow);
+        day = load_day_row(P, t_day);
+        // (d) reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
+        const double c_gas = __hiloint2double(q0.y, q0.x), c_eua = __hiloint2double(q0.w, q0.z);
+        const double c_el = __hiloint2double(q1.y, q1.x), c_0 = __hiloint2double(q1.w, q1.z);
+        double rew = __fma_rn(c_gas, day.gas, __fma_rn(c_eua, day.eua, __fma_rn(-c_el, hour_row_el<NV>(hrow), c_0)));
+        if (state_change) rew -= P.penalty;
+        ep_ret += rew;
+        reward = (float)rew;
+        o.norm[0] = __int_as_float(q2.x); o.norm[1] = __int_as_float(q2.y); o.norm[2] = __int_as_float(q2.z);
+        o.norm[3] = __int_as_float(q2.w); o.norm[4] = __int_as_float(q3.x); o.norm[5] = __int_as_float(q3.y);
+        tinfo = q3.z;
+        o.status = m.state;
+        o.sin_h = __int_as_float(c4.x); o.cos_h = __int_as_float(c4.y);
+        uint32_t nchg = 0;
+        if (P.has_penalty) { nchg = P.nchg[e] + (uint32_t)state_change; P.nchg[e] = nchg; }
+        done = (k == P.eps_sim_steps - 6);            // :508-511 (k before the increment)
+        if (EVAL && io.info != nullptr)
+            write_info<NV>(P, io.info, e, InfoKey{k, t_hour, t_day, ent, state_change, meta, rew,
+                                                  ep_ret + (double)nchg * P.penalty});
+        k += 1;
+        if (done) {                                   // SB3 auto-reset (DummyVecEnv.step_wait), out of line
+            finish_episode<NV, MOD>(P, io, e, single, k, ep_ret, m.cur_action, ObsKey{ent, t_hour, t_day, m.state, k});
+            const int4 core = P.core[e];              // the reset state written by finish_episode
+            tinfo = P.tinfo[e]; ep = P.ep[e];
+            i = core.x; j = core.y; k = core.z; meta = (uint32_t)core.w; ep_ret = 0.0;
+            t_hour = ep.x; t_day = ep.y;
+            clamp_market_index(P, t_hour, t_day);
+            load_hour_row<NV>(P, t_hour, hrow);
+            day = load_day_row(P, t_day);
+            o.status = PTG_COOLDOWN;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) o.norm[q] = P.reset_norm[q];
+            o.sin_h = 0.0f; o.cos_h = 1.0f;
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) hrow[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        day = DayRow{};
+        o = ObsRegs{};
+    }
+    emit_obs<NV, MOD>(P, obs_out, sm, e, active, lane, warp_env0, nvalid, hrow, day, o);
+    if (active) {
+        rew_out[e] = reward;
+        done_out[e] = (uint8_t)done;
+    }
+}
+
+// VecEnv.step_wait(): MANY = false -> exactly one step (ptg_step); MANY = true -> T steps with the plant state
+// kept in registers between steps (ptg_step_many).  EVAL = the 24-field info of train_or_eval == "eval".
+template <int NV, bool MOD, bool MANY, bool EVAL>
+__global__ void __launch_bounds__(PTG_BLOCK, PTG_STEP_MIN_BLOCKS)
+k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, int adtype,
+       const __grid_constant__ PtgIO io, int T) {
     __shared__ __align__(16) float stage[PTG_BLOCK / 32][32 * 4 * NV];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -469,104 +598,34 @@ __global__ void __launch_bounds__(PTG_BLOCK) k_step(const __grid_constant__ DevP
     const bool active = e < P.n_envs;
     const int64_t le = active ? e : P.n_envs - 1;       // tail lanes shadow the last env (no stores)
 
-    int4 core = P.core[le];
+    const int4 core = P.core[le];
     int32_t tinfo = P.tinfo[le];
     int2 ep = P.ep[le];
     double ep_ret = P.ep_ret[le];
-    Meta m = meta_unpack((uint32_t)core.w);
     int i = core.x, j = core.y, k = core.z;
-
-    for (int t = 0; t < T; ++t) {
-        float4 hrow[NV];
-        DayRow day;
-        ObsRegs o;
-        float reward = 0.f;
-        int done = 0;
-        if (active) {
-            const int action = decode_action(P, actions, adtype, (int64_t)t * P.n_envs + e, m.cur_action);
-            const int prev_state = m.state;
-            const int ent = plant_transition(P, e, action, i, j, m, tinfo);
-            // step-table entry: 5 x 16 B
-            const int4* ep4 = reinterpret_cast<const int4*>(P.step_tab + ent);
-            const int4 q0 = __ldg(ep4), q1 = __ldg(ep4 + 1), q2 = __ldg(ep4 + 2), q3 = __ldg(ep4 + 3), q4 = __ldg(ep4 + 4);
-            double mean[5];
-            mean[0] = __hiloint2double(q0.y, q0.x); mean[1] = __hiloint2double(q0.w, q0.z);
-            mean[2] = __hiloint2double(q1.y, q1.x); mean[3] = __hiloint2double(q1.w, q1.z);
-            mean[4] = __hiloint2double(q2.y, q2.x);
-            const double t_end = __hiloint2double(q2.w, q2.z);
-            o.norm[0] = __int_as_float(q3.x); o.norm[1] = __int_as_float(q3.y); o.norm[2] = __int_as_float(q3.z);
-            o.norm[3] = __int_as_float(q3.w); o.norm[4] = __int_as_float(q4.x); o.norm[5] = __int_as_float(q4.y);
-            tinfo = q4.z;
-            // clock + market rows of the NEW hour/day (:442-447)
-            const int4 c4 = __ldg(reinterpret_cast<const int4*>(P.clock_tab + (k + 1)));
-            o.sin_h = __int_as_float(c4.x); o.cos_h = __int_as_float(c4.y);
-            int t_hour = ep.x + c4.z, t_day = ep.y + c4.w;
-            clamp_market_index(P, t_hour, t_day);
-            load_hour_row<NV>(P, t_hour, hrow);
-            day = load_day_row(P, t_day);
-            o.status = m.state;
-            // reward (:463-468)
-            RewardParts r;
-            const int state_change = (prev_state != m.state);
-            reward_parts(P, mean, hour_row_el<NV>(hrow), day.gas, day.eua, state_change, r);
-            ep_ret += r.rew;
-            reward = (float)r.rew;
-            uint32_t nchg = 0;
-            if (P.has_penalty) { nchg = P.nchg[e] + (uint32_t)state_change; P.nchg[e] = nchg; }
-            done = (k == P.eps_sim_steps - 6);            // :508-511 (k before the increment)
-            if (io.info != nullptr && P.eval_mode && T == 1) {
-                InfoSnap s;
-                s.k = k; s.t_hour = t_hour; s.state = m.state; s.cur_action = m.cur_action; s.hot_cold = m.hot_cold;
-                s.el = hour_row_el<NV>(hrow); s.gas = day.gas; s.eua = day.eua; s.t_cat = t_end;
-                s.cum_rew = ep_ret + (double)nchg * P.penalty;
-#pragma unroll
-                for (int q = 0; q < 5; ++q) s.flow[q] = mean[q];
-                s.r = r;
-                write_info(P, io.info, e, s);
-            }
-            k += 1;
-            if (done) {                                   // SB3 auto-reset (DummyVecEnv.step_wait)
-                if (T == 1) {
-                    if (io.terminal_obs != nullptr) emit_obs_scalar<NV, MOD>(P, io.terminal_obs, e, make_snap<NV>(hrow, day, o));
-                    if (io.episode_return != nullptr) io.episode_return[e] = ep_ret;
-                    if (io.episode_length != nullptr) io.episode_length[e] = k;
-                }
-                P.fin_cnt[e] += 1;
-                P.fin_ret_sum[e] += ep_ret;
-                P.fin_ret_sq[e] += ep_ret * ep_ret;
-                P.fin_len_sum[e] += (double)k;
-                P.fin_min[e] = fmin(P.fin_min[e], ep_ret);
-                P.fin_max[e] = fmax(P.fin_max[e], ep_ret);
-                const int32_t mc = P.ep_count[e] + 1;
-                P.ep_count[e] = mc;
-                env_reset_state(P, e, mc, core, tinfo, ep, m);
-                P.ep[e] = ep;
-                if (P.has_penalty) P.nchg[e] = 0;
-                i = core.x; j = 0; k = 0; ep_ret = 0.0;
-                t_hour = ep.x; t_day = ep.y;
-                clamp_market_index(P, t_hour, t_day);
-                load_hour_row<NV>(P, t_hour, hrow);
-                day = load_day_row(P, t_day);
-                o.status = PTG_COOLDOWN;
-#pragma unroll
-                for (int q = 0; q < 6; ++q) o.norm[q] = P.reset_norm[q];
-                o.sin_h = 0.0f; o.cos_h = 1.0f;
-            }
-        } else {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) hrow[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            day = DayRow{};
-            o = ObsRegs{};
-        }
-        float* obs_t = io.obs + (int64_t)t * P.obs_elems;
-        emit_obs<NV, MOD>(P, obs_t, stage[wid], e, active, lane, warp_env0, nvalid, hrow, day, o);
-        if (active) {
-            io.reward[(int64_t)t * P.n_envs + e] = reward;
-            io.done[(int64_t)t * P.n_envs + e] = (uint8_t)done;
+    uint32_t meta = (uint32_t)core.w;
+    {   // pull the plant state of the CTA that will run one scheduling wave later into L2 (fire and forget)
+        const int64_t pe = e + (int64_t)P.prefetch_distance;
+        if (pe < P.n_envs) {
+            prefetch_l2(P.core + pe);
+            if ((lane & 3) == 0) prefetch_l2(P.ep_ret + pe);
+            if ((lane & 3) == 1) prefetch_l2(P.ep + pe);
+            if ((lane & 7) == 2) prefetch_l2(P.tinfo + pe);
+            if (!MANY && (lane & 3) == 3) prefetch_l2(reinterpret_cast<const char*>(actions) + pe * P.action_bytes);
         }
     }
+
+    if (!MANY) {
+        step_one<NV, MOD, EVAL>(P, io, actions, adtype, e, true, e, active, lane, warp_env0, nvalid, stage[wid], io.obs,
+                          io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
+    } else {
+        for (int t = 0; t < T; ++t)
+            step_one<NV, MOD, false>(P, io, actions, adtype, (int64_t)t * P.n_envs + e, false, e, active, lane, warp_env0,
+                              nvalid, stage[wid], io.obs + (int64_t)t * P.obs_elems, io.reward + (int64_t)t * P.n_envs,
+                              io.done + (int64_t)t * P.n_envs, i, j, k, meta, tinfo, ep, ep_ret);
+    }
     if (active) {
-        P.core[e] = make_int4(i, j, k, (int)meta_pack(m));
+        P.core[e] = make_int4(i, j, k, (int)meta);
         P.tinfo[e] = tinfo;
         P.ep_ret[e] = ep_ret;
     }

@@ -139,10 +139,14 @@ class PtGVecEnv(_Base):
         self._ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
         self._ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._obs_dict = self._obs_views(self._obs)          # views are created once; buffers are reused
         self._io = self._make_io(self._obs, self._reward, self._done, self._term_obs,
                                  self._info if self.cfg.train_or_eval else None, self._ep_ret, self._ep_len)
         # pinned host mirrors for the numpy API
-        self._obs_h = torch.zeros(self.obs_elems, dtype=torch.float32).pin_memory()
+        # two host observation buffers used alternately: the dict returned by step t stays valid until step
+        # t + 2, which is what SB3's collect_rollouts needs (it stores the previous obs after the next step)
+        self._obs_hh = [torch.zeros(self.obs_elems, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._flip = 0
         self._term_obs_h = torch.zeros(self.obs_elems, dtype=torch.float32).pin_memory()
         self._reward_h = torch.zeros(n, dtype=torch.float32).pin_memory()
         self._done_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
@@ -194,8 +198,12 @@ class PtGVecEnv(_Base):
             a = views[name].numpy()
             if rows is not None:
                 a = a[rows]
-            out[name] = a.astype(np.int64) if is_int else a.astype(self.obs_dtype, copy=True)
+            out[name] = a.astype(np.int64) if is_int else a.astype(self.obs_dtype, copy=False)
         return out
+
+    def _next_obs_host(self) -> torch.Tensor:
+        self._flip ^= 1
+        return self._obs_hh[self._flip]
 
     def _check_open(self):
         if self._h is None:
@@ -216,16 +224,16 @@ class PtGVecEnv(_Base):
         return list(self._seeds)
 
     def reset(self):
-        obs = self.reset_tensor(_return_views=False)
-        self._obs_h.copy_(self._obs, non_blocking=True)
+        self.reset_tensor(_return_views=False)
+        obs_h = self._next_obs_host()
+        obs_h.copy_(self._obs, non_blocking=True)
         want_info = self.num_envs <= self.info_limit
         if want_info:
             self._info_h.copy_(self._info, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         self.poll_error()
         self.reset_infos = self._info_dicts(range(self.num_envs)) if want_info else [{} for _ in range(self.num_envs)]
-        del obs
-        return self._obs_numpy(self._obs_h)
+        return self._obs_numpy(obs_h)
 
     def step_async(self, actions) -> None:
         self._check_open()
@@ -240,7 +248,8 @@ class PtGVecEnv(_Base):
                                     C.byref(self._io), self._stream()))
 
     def step_wait(self):
-        self._obs_h.copy_(self._obs, non_blocking=True)
+        obs_h = self._next_obs_host()
+        obs_h.copy_(self._obs, non_blocking=True)
         self._reward_h.copy_(self._reward, non_blocking=True)
         self._done_h.copy_(self._done, non_blocking=True)
         eval_mode = bool(self.cfg.train_or_eval)
@@ -266,7 +275,7 @@ class PtGVecEnv(_Base):
                 d["TimeLimit.truncated"] = False                     # the env only ever terminates (:478-481)
                 d["terminal_observation"] = {k: v[q] for k, v in term.items()}
                 infos[e] = d
-        return self._obs_numpy(self._obs_h), self._reward_h.numpy().copy(), dones, infos
+        return self._obs_numpy(obs_h), self._reward_h.numpy().copy(), dones, infos
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None:
@@ -352,7 +361,7 @@ class PtGVecEnv(_Base):
         io = self._make_io(self._obs, None, None, None, self._info)
         _lib.check(self._L.ptg_reset(self._h, seeds_p, mask_p, C.byref(io), self._stream()))
         self._reset_seeds()
-        return self._obs_views(self._obs) if _return_views else None
+        return self._obs_dict if _return_views else None
 
     def step_tensor(self, actions: torch.Tensor):
         """One step on device: ``actions`` is a CUDA tensor [n_envs] (int64/int32/uint8, or float32 for
@@ -362,7 +371,7 @@ class PtGVecEnv(_Base):
         if a.device != self.device or a.numel() != self.num_envs or not a.is_contiguous():
             raise ValueError("actions must be a contiguous CUDA tensor with n_envs elements on the env's device")
         _lib.check(self._L.ptg_step(self._h, self._ptr(a), _TORCH_ACT[a.dtype], C.byref(self._io), self._stream()))
-        return self._obs_views(self._obs), self._reward, self._done
+        return self._obs_dict, self._reward, self._done
 
     def rollout_tensor(self, actions: torch.Tensor, out: dict | None = None):
         """T steps in ONE launch (state stays in registers): ``actions`` is [T, n_envs] on device.  Returns a dict
