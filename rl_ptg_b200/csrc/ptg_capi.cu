@@ -73,9 +73,16 @@ template <int NV, bool MOD>
 void launch_step_t(PtgHandle* h, const void* actions, int adtype, const PtgIO& io, int T, cudaStream_t st) {
     const unsigned grid = blocks_for(h->P.n_envs, PTG_BLOCK);
     h->P.action_bytes = adtype == PTG_ACT_I64 ? 8 : adtype == PTG_ACT_U8 ? 1 : 4;
-    if (T > 0) k_step<NV, MOD, true, false><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, T);
-    else if (h->P.eval_mode && io.info) k_step<NV, MOD, false, true><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, 1);
-    else k_step<NV, MOD, false, false><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, 1);
+    const bool pa13 = NV == 4 && h->P.pa == 13;       // compile-time price_ahead for the reference default
+    if (T > 0) {
+        if (pa13) k_step<NV, MOD, true, false, (NV == 4 ? 13 : 0)><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, T);
+        else k_step<NV, MOD, true, false, 0><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, T);
+    } else if (h->P.eval_mode && io.info) {
+        k_step<NV, MOD, false, true, 0><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, 1);
+    } else {
+        if (pa13) k_step<NV, MOD, false, false, (NV == 4 ? 13 : 0)><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, 1);
+        else k_step<NV, MOD, false, false, 0><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, 1);
+    }
 }
 template <int NV, bool MOD>
 void launch_reset_t(PtgHandle* h, const int64_t* seeds, const uint8_t* mask, const PtgIO& io, cudaStream_t st) {
@@ -317,8 +324,7 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     const size_t n = (size_t)n_envs;
     PTG_TRY(h->alloc(&P.core, n)); PTG_TRY(h->alloc(&P.tinfo, n)); PTG_TRY(h->alloc(&P.ep, n));
     PTG_TRY(h->alloc(&P.ep_ret, n)); PTG_TRY(h->alloc(&P.ep_count, n)); PTG_TRY(h->alloc(&P.ep_start, n));
-    PTG_TRY(h->alloc(&P.nchg, n)); PTG_TRY(h->alloc(&P.rng_state, n)); PTG_TRY(h->alloc(&P.rng_inc, n));
-    PTG_TRY(h->alloc(&P.draws, n));
+    PTG_TRY(h->alloc(&P.nchg, n)); PTG_TRY(h->alloc(&P.rng, n));
     PTG_TRY(h->alloc(&P.fin_cnt, n)); PTG_TRY(h->alloc(&P.fin_ret_sum, n)); PTG_TRY(h->alloc(&P.fin_ret_sq, n));
     PTG_TRY(h->alloc(&P.fin_len_sum, n)); PTG_TRY(h->alloc(&P.fin_min, n)); PTG_TRY(h->alloc(&P.fin_max, n));
     PTG_TRY(h->alloc(&h->d_seeds, n)); PTG_TRY(h->alloc(&h->d_mask, n));

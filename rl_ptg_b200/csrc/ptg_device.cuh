@@ -75,6 +75,16 @@ struct RewardConsts {
     int32_t b_s3, _pad;
 };
 
+// --- per-env noise generator: ONE 64 B line; sector 0 is read-modify-written by a draw, sector 1 is constant ---
+struct __align__(16) RngRec {
+    uint64_t s_hi, s_lo;   // PCG64 state
+    int64_t draws;         // normal draws consumed so far (tape position in tape mode)
+    uint64_t _pad0;
+    uint64_t i_hi, i_lo;   // PCG64 increment
+    uint64_t _pad1, _pad2;
+};
+static_assert(sizeof(RngRec) == 64, "RngRec layout");
+
 // --- everything a kernel needs, passed by value (__grid_constant__) ---------------------------------------------
 struct DevParams {
     // sizes
@@ -131,9 +141,7 @@ struct DevParams {
     int32_t* ep_count;             // constructor/resets consumed (m)
     int32_t* ep_start;             // SUBPROC schedule: start offset
     uint32_t* nchg;                // state changes this episode (only maintained when has_penalty)
-    ulonglong2* rng_state;         // PCG64 state (hi, lo)
-    ulonglong2* rng_inc;           // PCG64 increment (hi, lo)
-    int64_t* draws;                // normal draws consumed
+    RngRec* rng;                   // per-env generator record (one 64 B line)
     const double* tape;            // tape-mode noise [n_envs][tape_len]
     int64_t tape_len;
     // finished-episode accumulators
@@ -179,16 +187,19 @@ __device__ __forceinline__ int cur_table(const Meta& m) {
 // footprint of every thread of the step kernel.
 __device__ __noinline__ double draw_noise(const DevParams& P, int64_t e) {
     if (P.noise_mode == PTG_NOISE_OFF) return 0.0;
-    int64_t d = P.draws[e];
-    P.draws[e] = d + 1;
+    ulonglong2* rec = reinterpret_cast<ulonglong2*>(P.rng + e);
+    const ulonglong2 st = rec[0], dr = rec[1];
+    const int64_t d = (int64_t)dr.x;
     if (P.noise_mode == PTG_NOISE_TAPE) {
+        rec[1] = make_ulonglong2((unsigned long long)(d + 1), 0ull);
         if (d >= P.tape_len) { atomicOr(P.err, PTG_EBIT_TAPE); return 0.0; }
         return P.tape[e * P.tape_len + d];
     }
-    ulonglong2 s = P.rng_state[e], inc = P.rng_inc[e];
-    Pcg64 g = {s.x, s.y, inc.x, inc.y};
-    double z = pcg64_standard_normal(g, P.zig);
-    P.rng_state[e] = make_ulonglong2(g.s_hi, g.s_lo);
+    const ulonglong2 inc = rec[2];
+    Pcg64 g = {st.x, st.y, inc.x, inc.y};
+    const double z = pcg64_standard_normal(g, P.zig);
+    rec[0] = make_ulonglong2(g.s_hi, g.s_lo);
+    rec[1] = make_ulonglong2((unsigned long long)(d + 1), 0ull);
     return 0.0 + P.noise * z;      // random_normal: loc + scale * standard_normal
 }
 

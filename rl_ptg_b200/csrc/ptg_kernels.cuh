@@ -171,8 +171,9 @@ __global__ void k_build_hour_tab(const double* e_r_b, int n_hours, int pa, int n
         double v = e_r_b[((int64_t)src * pa + a) * n_hours + t];
         row[a] = (float)((v - lo) / (hi - lo));
         double pf = e_r_b[((int64_t)2 * pa + a) * n_hours + t];
-        int code = (pf == -1.0) ? 0 : (pf == 0.0) ? 1 : (pf == 1.0) ? 2 : 3;
-        if (code == 3 && !raw) atomicOr(err, PTG_EBIT_PARTFULL);
+        const bool ok = (pf == -1.0) || (pf == 0.0) || (pf == 1.0);
+        if (!ok && !raw) atomicOr(err, PTG_EBIT_PARTFULL);
+        const int code = ok ? (int)pf : 0;                 // 2-bit two's complement: -1 -> 0b11, 0 -> 0b00, 1 -> 0b01
         bits |= (uint32_t)(code & 3) << (2 * a);
     }
     for (int a = pa; a < nv * 4 - 3; ++a) row[a] = 0.f;
@@ -216,38 +217,68 @@ struct ObsRegs {            // what one env contributes to the observation, in r
     float sin_h, cos_h;
 };
 
-// Coalesced store of one [n_envs, pa] block: per-warp transpose through shared memory, 16-byte global stores.
-template <int NV>
-__device__ __forceinline__ void store_window_block(float* __restrict__ dst, float* sm, const float (&w)[4 * NV],
-                                                   int pa, int lane, int64_t warp_env0, int nvalid) {
-#pragma unroll
-    for (int a = 0; a < 4 * NV; ++a)
-        if (a < pa) sm[lane * pa + a] = w[a];
-    __syncwarp();
-    float* g = dst + warp_env0 * pa;
-    if (nvalid == 32) {
-        const float4* s4 = reinterpret_cast<const float4*>(sm);
-        float4* g4 = reinterpret_cast<float4*>(g);
-        for (int idx = lane; idx < 8 * pa; idx += 32) g4[idx] = s4[idx];
-    } else {
-        for (int idx = lane; idx < nvalid * pa; idx += 32) g[idx] = sm[idx];
-    }
-    __syncwarp();
+// --- TMA (bulk async copy) helpers: shared::cta -> global, 1-D ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory (the staging buffer may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int NV, bool MOD>
-__device__ __forceinline__ void emit_obs(const DevParams& P, float* __restrict__ obs, float* sm, int64_t e,
-                                         bool active, int lane, int64_t warp_env0, int nvalid,
-                                         const float4 (&hrow)[NV], const DayRow& day, const ObsRegs& o) {
+#define PTG_STAGE_FLOATS(NV) (32 * (4 * (NV) - 3))   // one [32 envs][pa <= 4*NV-3 values] staging region of a warp
+
+// Observation emission.  The two [n_envs, price_ahead] blocks are transposed per warp through shared memory
+// ([32][pa] floats, stride pa: conflict free for odd pa) and leave the SM as ONE bulk async copy (TMA) per block
+// and warp -- 128*pa contiguous bytes -- issued by lane 0; the nine scalar keys are plain coalesced stores.
+// PAC > 0 fixes price_ahead at compile time (the reference default 13) so the staging stores need no predicates.
+template <int NV, bool MOD, int PAC>
+__device__ __forceinline__ void stage_windows(const DevParams& P, float* sm, int lane, const float4 (&hrow)[NV]) {
+    const int pa = PAC > 0 ? PAC : P.pa;
+    if (lane == 0) tma_store_wait_read();         // previous step's bulk stores (rollout kernel) are done with sm
+    __syncwarp();
     float w[4 * NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) { w[4 * v] = hrow[v].x; w[4 * v + 1] = hrow[v].y; w[4 * v + 2] = hrow[v].z; w[4 * v + 3] = hrow[v].w; }
-    store_window_block<NV>(obs + P.off_win0, sm, w, P.pa, lane, warp_env0, nvalid);
-    if (MOD) {
-        const uint32_t bits = __float_as_uint(w[4 * NV - 3]);
+    float* rowA = sm + lane * pa;
 #pragma unroll
-        for (int a = 0; a < 4 * NV; ++a) w[a] = (float)((bits >> (2 * a)) & 3u) - 1.0f;     // Part_Full, :239
-        store_window_block<NV>(obs + P.off_win1, sm, w, P.pa, lane, warp_env0, nvalid);
+    for (int a = 0; a < 4 * NV - 3; ++a)
+        if (a < pa) rowA[a] = w[a];
+    if (MOD) {
+        // Part_Full (:239): 2-bit two's-complement codes (-1, 0, +1) -> sign-extending bit-field extract
+        const int bits = __float_as_int(w[4 * NV - 3]);
+        float* rowB = sm + PTG_STAGE_FLOATS(NV) + lane * pa;
+#pragma unroll
+        for (int a = 0; a < 16 && a < 4 * NV - 3; ++a)
+            if (a < pa) rowB[a] = (float)((bits << (30 - 2 * a)) >> 30);
+    }
+}
+
+template <int NV, bool MOD, int PAC>
+__device__ __forceinline__ void flush_obs(const DevParams& P, float* __restrict__ obs, float* sm, int64_t e,
+                                          bool active, int lane, int64_t warp_env0, int nvalid, const DayRow& day,
+                                          const ObsRegs& o) {
+    const int pa = PAC > 0 ? PAC : P.pa;
+    float* smA = sm;
+    float* smB = sm + PTG_STAGE_FLOATS(NV);
+    float* gA = obs + P.off_win0 + warp_env0 * pa;
+    float* gB = obs + P.off_win1 + warp_env0 * pa;
+    if (nvalid == 32) {
+        fence_proxy_async_smem();                 // make the generic-proxy writes visible to the async proxy
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_1d(gA, smA, 128u * (uint32_t)pa);
+            if (MOD) tma_store_1d(gB, smB, 128u * (uint32_t)pa);
+            tma_store_commit();
+        }
+    } else {                                      // ragged last warp: plain stores
+        __syncwarp();
+        for (int idx = lane; idx < nvalid * pa; idx += 32) {
+            gA[idx] = smA[idx];
+            if (MOD) gB[idx] = smB[idx];
+        }
     }
     if (!active) return;
     if (!MOD) {
@@ -260,6 +291,14 @@ __device__ __forceinline__ void emit_obs(const DevParams& P, float* __restrict__
     for (int q = 0; q < 6; ++q) sc[(1 + q) * P.n_pad] = o.norm[q];
     sc[7 * P.n_pad] = o.sin_h;
     sc[8 * P.n_pad] = o.cos_h;
+}
+
+template <int NV, bool MOD>
+__device__ __forceinline__ void emit_obs(const DevParams& P, float* __restrict__ obs, float* sm, int64_t e,
+                                         bool active, int lane, int64_t warp_env0, int nvalid,
+                                         const float4 (&hrow)[NV], const DayRow& day, const ObsRegs& o) {
+    stage_windows<NV, MOD, 0>(P, sm, lane, hrow);
+    flush_obs<NV, MOD, 0>(P, obs, sm, e, active, lane, warp_env0, nvalid, day, o);
 }
 
 // Everything one env contributes to an observation can be re-derived from five integers: the step-table entry
@@ -277,7 +316,7 @@ __device__ __noinline__ void emit_obs_scalar(const DevParams& P, float* __restri
     for (int a = 0; a < P.pa; ++a) obs[P.off_win0 + e * P.pa + a] = w[a];
     if (MOD) {
         const uint32_t bits = __float_as_uint(w[4 * NV - 3]);
-        for (int a = 0; a < P.pa; ++a) obs[P.off_win1 + e * P.pa + a] = (float)((bits >> (2 * a)) & 3u) - 1.0f;
+        for (int a = 0; a < P.pa; ++a) obs[P.off_win1 + e * P.pa + a] = (float)(((int)bits << (30 - 2 * a)) >> 30);
     } else {
         const DayRow day = P.day_tab[key.t_day];
         obs[P.off_gas + 2 * e] = day.gas_n0; obs[P.off_gas + 2 * e + 1] = day.gas_n1;
@@ -386,9 +425,9 @@ __global__ void k_construct(const __grid_constant__ DevParams P) {
     // The reference's generator is unseeded until reset(seed=...) (gymnasium); we start every env from
     // SeedSequence(global id) so that an unseeded run is still reproducible.
     Pcg64 g = pcg64_from_seed((uint64_t)gid);
-    P.rng_state[e] = make_ulonglong2(g.s_hi, g.s_lo);
-    P.rng_inc[e] = make_ulonglong2(g.i_hi, g.i_lo);
-    P.draws[e] = 0;
+    RngRec rr = {};
+    rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo; rr.draws = 0;
+    P.rng[e] = rr;
     if (P.schedule_mode == PTG_SCHED_SUBPROC) {
         // :43-44 draws ep_index from an UNSEEDED generator per worker process; here: a fixed stream per global id
         Pcg64 h = pcg64_from_seed(0x5eed0000ull + (uint64_t)gid);
@@ -410,7 +449,7 @@ __global__ void k_construct(const __grid_constant__ DevParams P) {
 template <int NV, bool MOD>
 __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ DevParams P, const int64_t* seeds,
                                                      const uint8_t* mask, const __grid_constant__ PtgIO io) {
-    __shared__ __align__(16) float stage[PTG_BLOCK / 32][32 * 4 * NV];
+    __shared__ __align__(128) float stage[PTG_BLOCK / 32][2 * PTG_STAGE_FLOATS(NV)];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t warp_env0 = e - lane;
@@ -428,9 +467,9 @@ __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ Dev
     if (doit) {
         if (seeds != nullptr && seeds[e] >= 0) {          // gymnasium Env.reset(seed=...)
             Pcg64 g = pcg64_from_seed((uint64_t)seeds[e]);
-            P.rng_state[e] = make_ulonglong2(g.s_hi, g.s_lo);
-            P.rng_inc[e] = make_ulonglong2(g.i_hi, g.i_lo);
-            P.draws[e] = 0;
+            RngRec rr = {};
+            rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo; rr.draws = 0;
+            P.rng[e] = rr;
         }
         m = meta_unpack((uint32_t)P.core[e].w);
         const int32_t mc = P.ep_count[e] + 1;
@@ -451,6 +490,7 @@ __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ Dev
         if (mask == nullptr) emit_obs<NV, MOD>(P, io.obs, stage[wid], e, active, lane, warp_env0, nvalid, hrow, day, o);
         else if (doit) emit_obs_scalar<NV, MOD>(P, io.obs, e, ObsKey{-1, t_hour, t_day, PTG_COOLDOWN, 0});
     }
+    if (lane == 0) tma_store_wait_read();
     if (doit && io.info != nullptr) {
         write_info<NV>(P, io.info, e, InfoKey{0, t_hour, t_day, -1, 0, meta_pack(m), 0.0, 0.0});
     }
@@ -492,55 +532,77 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// One env step of one thread.  Register discipline: only the packed plant state is live across the (branchy,
-// possibly calling) plant transition; the market rows are *prefetched* into L1 before it and loaded after it.
-template <int NV, bool MOD, bool EVAL>
-__device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, const void* __restrict__ actions,
-                                         int adtype, int64_t act_idx, bool single, int64_t e, bool active, int lane,
-                                         int64_t warp_env0, int nvalid, float* sm, float* __restrict__ obs_out,
+__device__ __forceinline__ long long load_action_raw(const void* __restrict__ actions, int adtype, int64_t idx) {
+    if (adtype == PTG_ACT_I64) return __ldg((const long long*)actions + idx);
+    if (adtype == PTG_ACT_I32) return __ldg((const int*)actions + idx);
+    if (adtype == PTG_ACT_U8) return __ldg((const unsigned char*)actions + idx);
+    return (long long)__float_as_int(__ldg((const float*)actions + idx));      // F32: raw bits
+}
+
+// Decode the action of an env (discrete id, or continuous Box(-1,1) -> 5 bins, :346-355) from load_action_raw.
+__device__ __forceinline__ int decode_action_raw(const DevParams& P, long long raw, int adtype, int prev_action) {
+    if (!P.continuous) {
+        long long a = adtype == PTG_ACT_F32 ? (long long)__int_as_float((int)raw) : raw;
+        if (a < 0 || a > 4) { atomicOr(P.err, PTG_EBIT_ACTION); a = PTG_COOLDOWN; }
+        return (int)a;
+    }
+    const double a = (double)__int_as_float((int)raw);
+    int act = prev_action;                        // a >= 1.0: no interval matches, previous action is kept
+#pragma unroll
+    for (int ival = 5; ival >= 0; --ival)
+        if (P.prob_thre[ival] > a) act = (ival + 4) % 5;   // first matching ival wins (descending scan)
+    return act;
+}
+
+// One env step of one thread.  Ordering (each group only depends on the ones above it):
+//   1. argmin-LUT gather + prefetch of the RNG line      <- only needs (state, action)
+//   2. clock row -> market rows -> stage the two observation windows in shared memory (independent of the
+//      plant transition: covers the latency of 1.)
+//   3. plant transition (may draw noise) -> step-table entry gather -> reward, scalars
+//   4. bulk stores
+template <int NV, bool MOD, bool EVAL, int PAC>
+__device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, long long action_raw, int adtype,
+                                         bool single, int64_t e, bool active, int lane, int64_t warp_env0,
+                                         int nvalid, float* sm, float* __restrict__ obs_out,
                                          float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int& i, int& j,
                                          int& k, uint32_t& meta, int32_t& tinfo, int2& ep, double& ep_ret) {
     float4 hrow[NV];
     DayRow day;
     ObsRegs o;
     float reward = 0.f;
-    int done = 0;
+    int done = 0, t_hour_out = 0;
     if (active) {
-        // (a) clock row of step k+1 -> market row indices of the NEW hour/day (:442-447); warm L1 with them
-        const int4 c4 = __ldg(reinterpret_cast<const int4*>(P.clock_tab + (k + 1)));
-        int t_hour = ep.x + c4.z, t_day = ep.y + c4.w;
-        clamp_market_index(P, t_hour, t_day);
-        {
-            const char* hp = reinterpret_cast<const char*>(P.hour_tab + (int64_t)t_hour * NV);
-#pragma unroll
-            for (int b = 0; b < NV * 16; b += 32) prefetch_l1(hp + b);
-            prefetch_l1(P.day_tab + t_day);
-        }
-        // (b) plant transition -> step-table entry.  The argmin-LUT gather and the RNG-state lines are requested
-        //     first, so their latency overlaps the clock/market prefetches above and the branchy code below.
+        // (1) what the transition will need from memory
         Meta m = meta_unpack(meta);
-        const int action = decode_action(P, actions, adtype, act_idx, m.cur_action);
-        const int prev_state = m.state;
+        const int action = decode_action_raw(P, action_raw, adtype, m.cur_action);
         int will_draw;
         const int col = argmin_column(action, m, tinfo & 7, will_draw);
         int lut_val = 0;
         if (col >= 0) lut_val = __ldg(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + col);
-        if (will_draw && P.noise_mode != PTG_NOISE_OFF) {
-            prefetch_l1(P.draws + e);
-            if (P.noise_mode == PTG_NOISE_NUMPY) { prefetch_l1(P.rng_state + e); prefetch_l1(P.rng_inc + e); }
-        }
-        const int ent = plant_transition(P, e, action, i, j, m, tinfo, lut_val);
-        meta = meta_pack(m);
-        const int state_change = (prev_state != m.state);
-        // (c) gathers: entry (4 x 16 B = two sectors), hour row, day row
-        const int4* ep4 = reinterpret_cast<const int4*>(P.step_tab + ent);
-        const int4 q0 = __ldg(ep4), q1 = __ldg(ep4 + 1), q2 = __ldg(ep4 + 2), q3 = __ldg(ep4 + 3);
+        if (will_draw && P.noise_mode != PTG_NOISE_OFF) prefetch_l1(P.rng + e);
+        // (2) clock row of step k+1 -> market rows of the NEW hour/day (:442-447) -> observation windows
+        const int4 c4 = __ldg(reinterpret_cast<const int4*>(P.clock_tab + (k + 1)));
+        int t_hour = ep.x + c4.z, t_day = ep.y + c4.w;
+        clamp_market_index(P, t_hour, t_day);
         load_hour_row<NV>(P, t_hour, hrow);
         day = load_day_row(P, t_day);
-        // (d) reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
+        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
+        const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
+        // (3) plant transition -> step-table entry (4 x 16 B = two sectors)
+        const int prev_state = m.state;
+#if defined(PTG_EXP_NO_TRANSITION)
+        j += 1; const int ent = P.ent_off[PTG_DS_COOLDOWN] + ((i + j + action) & 0x7fff); (void)lut_val;
+#else
+        const int ent = plant_transition(P, e, action, i, j, m, tinfo, lut_val);
+#endif
+        meta = meta_pack(m);
+        const int state_change = (prev_state != m.state);
+        const int4* ep4 = reinterpret_cast<const int4*>(P.step_tab + ent);
+        const int4 q0 = __ldg(ep4), q1 = __ldg(ep4 + 1), q2 = __ldg(ep4 + 2), q3 = __ldg(ep4 + 3);
+        // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
         const double c_gas = __hiloint2double(q0.y, q0.x), c_eua = __hiloint2double(q0.w, q0.z);
         const double c_el = __hiloint2double(q1.y, q1.x), c_0 = __hiloint2double(q1.w, q1.z);
-        double rew = __fma_rn(c_gas, day.gas, __fma_rn(c_eua, day.eua, __fma_rn(-c_el, hour_row_el<NV>(hrow), c_0)));
+        double rew = __fma_rn(c_gas, day.gas, __fma_rn(c_eua, day.eua, __fma_rn(-c_el, el, c_0)));
         if (state_change) rew -= P.penalty;
         ep_ret += rew;
         reward = (float)rew;
@@ -563,20 +625,30 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, co
             i = core.x; j = core.y; k = core.z; meta = (uint32_t)core.w; ep_ret = 0.0;
             t_hour = ep.x; t_day = ep.y;
             clamp_market_index(P, t_hour, t_day);
-            load_hour_row<NV>(P, t_hour, hrow);
             day = load_day_row(P, t_day);
             o.status = PTG_COOLDOWN;
 #pragma unroll
             for (int q = 0; q < 6; ++q) o.norm[q] = P.reset_norm[q];
             o.sin_h = 0.0f; o.cos_h = 1.0f;
         }
+        t_hour_out = t_hour;
     } else {
 #pragma unroll
         for (int v = 0; v < NV; ++v) hrow[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         day = DayRow{};
         o = ObsRegs{};
+        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
     }
-    emit_obs<NV, MOD>(P, obs_out, sm, e, active, lane, warp_env0, nvalid, hrow, day, o);
+    // episode ends are rare: only then is the warp's window tile staged again, from re-read hour rows (the reset
+    // observation of the done lanes, the unchanged rows of the others)
+    if (__any_sync(0xffffffffu, done)) {
+        float4 h2[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) h2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) load_hour_row<NV>(P, t_hour_out, h2);
+        stage_windows<NV, MOD, PAC>(P, sm, lane, h2);
+    }
+    flush_obs<NV, MOD, PAC>(P, obs_out, sm, e, active, lane, warp_env0, nvalid, day, o);
     if (active) {
         rew_out[e] = reward;
         done_out[e] = (uint8_t)done;
@@ -585,11 +657,11 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, co
 
 // VecEnv.step_wait(): MANY = false -> exactly one step (ptg_step); MANY = true -> T steps with the plant state
 // kept in registers between steps (ptg_step_many).  EVAL = the 24-field info of train_or_eval == "eval".
-template <int NV, bool MOD, bool MANY, bool EVAL>
+template <int NV, bool MOD, bool MANY, bool EVAL, int PAC>
 __global__ void __launch_bounds__(PTG_BLOCK, PTG_STEP_MIN_BLOCKS)
 k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, int adtype,
        const __grid_constant__ PtgIO io, int T) {
-    __shared__ __align__(16) float stage[PTG_BLOCK / 32][32 * 4 * NV];
+    __shared__ __align__(128) float stage[PTG_BLOCK / 32][2 * PTG_STAGE_FLOATS(NV)];
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t warp_env0 = e - lane;
@@ -602,6 +674,7 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     int32_t tinfo = P.tinfo[le];
     int2 ep = P.ep[le];
     double ep_ret = P.ep_ret[le];
+    long long action_raw = load_action_raw(actions, adtype, le);
     int i = core.x, j = core.y, k = core.z;
     uint32_t meta = (uint32_t)core.w;
     {   // pull the plant state of the CTA that will run one scheduling wave later into L2 (fire and forget)
@@ -616,19 +689,23 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     }
 
     if (!MANY) {
-        step_one<NV, MOD, EVAL>(P, io, actions, adtype, e, true, e, active, lane, warp_env0, nvalid, stage[wid], io.obs,
-                          io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
+        step_one<NV, MOD, EVAL, PAC>(P, io, action_raw, adtype, true, e, active, lane, warp_env0, nvalid, stage[wid],
+                                     io.obs, io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
     } else {
-        for (int t = 0; t < T; ++t)
-            step_one<NV, MOD, false>(P, io, actions, adtype, (int64_t)t * P.n_envs + e, false, e, active, lane, warp_env0,
-                              nvalid, stage[wid], io.obs + (int64_t)t * P.obs_elems, io.reward + (int64_t)t * P.n_envs,
-                              io.done + (int64_t)t * P.n_envs, i, j, k, meta, tinfo, ep, ep_ret);
+        for (int t = 0; t < T; ++t) {
+            const long long a_now = action_raw;
+            if (t + 1 < T) action_raw = load_action_raw(actions, adtype, (int64_t)(t + 1) * P.n_envs + le);   // next step's
+            step_one<NV, MOD, false, PAC>(P, io, a_now, adtype, false, e, active, lane, warp_env0, nvalid, stage[wid],
+                                          io.obs + (int64_t)t * P.obs_elems, io.reward + (int64_t)t * P.n_envs,
+                                          io.done + (int64_t)t * P.n_envs, i, j, k, meta, tinfo, ep, ep_ret);
+        }
     }
     if (active) {
         P.core[e] = make_int4(i, j, k, (int)meta);
         P.tinfo[e] = tinfo;
         P.ep_ret[e] = ep_ret;
     }
+    if (lane == 0) tma_store_wait_read();               // the staging buffer must outlive the bulk stores' reads
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -713,7 +790,7 @@ __global__ void k_state_unpack(const __grid_constant__ DevParams P, StateDev s, 
     s.partial_ds[e] = m.part_ds; s.full_ds[e] = m.full_ds; s.current_action[e] = m.cur_action;
     const int2 ep = P.ep[e];
     s.act_ep_h[e] = ep.x; s.act_ep_d[e] = ep.y; s.episode_count[e] = P.ep_count[e];
-    s.draws[e] = P.draws[e];
+    s.draws[e] = P.rng[e].draws;
     s.t_cat[e] = vals[P.tinfo[e] >> 3];
     s.cum_reward[e] = P.ep_ret[e];
 }
@@ -728,7 +805,7 @@ __global__ void k_state_pack(const __grid_constant__ DevParams P, StateDev s, co
     P.core[e] = make_int4(s.i[e], s.j[e], s.k[e], (int)meta_pack(m));
     P.ep[e] = make_int2(s.act_ep_h[e], s.act_ep_d[e]);
     P.ep_count[e] = s.episode_count[e];
-    P.draws[e] = s.draws[e];
+    P.rng[e].draws = s.draws[e];
     P.tinfo[e] = tinfo_of(B, s.t_cat[e]);        // t_cat must be a temperature present in the tables (or 16)
     P.ep_ret[e] = s.cum_reward[e];
 }
