@@ -178,13 +178,7 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     P.schedule_mode = c.schedule_mode;
     P.penalty = c.reward_level * c.state_change_penalty;                       // :332
     P.has_penalty = P.penalty != 0.0;
-    P.time1_start_p_f = c.time1_start_p_f; P.time2_start_f_p = c.time2_start_f_p; P.time_p_f = c.time_p_f;
-    P.time_f_p = c.time_f_p; P.time1_p_f_p = c.time1_p_f_p; P.time2_p_f_p = c.time2_p_f_p;
-    P.time3_p_f_p = c.time3_p_f_p; P.time34_p_f_p = c.time34_p_f_p; P.time4_p_f_p = c.time4_p_f_p;
-    P.time45_p_f_p = c.time45_p_f_p; P.time5_p_f_p = c.time5_p_f_p; P.time1_f_p_f = c.time1_f_p_f;
-    P.time2_f_p_f = c.time2_f_p_f; P.time23_f_p_f = c.time23_f_p_f; P.time3_f_p_f = c.time3_f_p_f;
-    P.time34_f_p_f = c.time34_f_p_f; P.time4_f_p_f = c.time4_f_p_f; P.time45_f_p_f = c.time45_f_p_f;
-    P.time5_f_p_f = c.time5_f_p_f; P.i_fully_developed = c.i_fully_developed; P.j_fully_developed = c.j_fully_developed;
+    P.i_fully_developed = c.i_fully_developed; P.j_fully_developed = c.j_fully_developed;
     P.noise = c.noise; P.eps_len_d = c.eps_len_d;
     RewardConsts& R = P.rc;
     R.convert_mol_to_Nm3 = c.convert_mol_to_Nm3; R.H_u_CH4 = c.H_u_CH4; R.H_u_H2 = c.H_u_H2; R.dt_water = c.dt_water;
@@ -283,6 +277,44 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     k_build_clock_tab<<<blocks_for(c.eps_sim_steps + 1, 128), 128>>>(c.eps_sim_steps + 1, c.sim_step, clock_tab);
     P.clock_tab = clock_tab;
     h->launches += 3;
+    {   // load-change chains of _partial/_full as tables over time_op (evaluated literally, any threshold order)
+        int top = 0;
+        for (int v : {c.time1_start_p_f, c.time2_start_f_p, c.time_p_f, c.time_f_p, c.time1_p_f_p, c.time2_p_f_p,
+                      c.time34_p_f_p, c.time45_p_f_p, c.time5_p_f_p, c.time1_f_p_f, c.time23_f_p_f, c.time34_f_p_f,
+                      c.time45_f_p_f, c.time5_f_p_f})
+            top = std::max(top, v);
+        top += 1;                                    // every time_op >= top takes the same branch as top
+        std::vector<uint32_t> chain((size_t)4 * (top + 1));
+        for (int t = 0; t <= top; ++t) {
+            uint32_t v;
+            // _partial, full_op == 'op2_start_f' (:637-647)
+            v = t < c.time2_start_f_p ? chain_pack(PTG_DS_OP1_START_P, PTG_CHAIN_J_ARGMIN, 0) : chain_pack(PTG_DS_OP8_F_P, PTG_CHAIN_J_ONE, 0);
+            chain[(size_t)PTG_CHAIN_P_FROM_OP2F * (top + 1) + t] = v;
+            // _partial, full_op == 'op3_p_f' (:648-683)
+            if (t < c.time1_p_f_p) v = chain_pack(PTG_DS_OP8_F_P, PTG_CHAIN_J_DEVELOPED, 0);
+            else if (c.time1_p_f_p < t && t < c.time2_p_f_p) v = chain_pack(PTG_DS_OP4_P_F_P_5, PTG_CHAIN_J_KEEP, 0);
+            else if (c.time2_p_f_p < t && t < c.time_p_f) v = chain_pack(PTG_DS_OP4_P_F_P_5, PTG_CHAIN_J_ONE, c.time2_p_f_p);
+            else if (c.time_p_f < t && t < c.time34_p_f_p) v = chain_pack(PTG_DS_OP5_P_F_P_10, PTG_CHAIN_J_ONE, c.time3_p_f_p);
+            else if (c.time34_p_f_p < t && t < c.time45_p_f_p) v = chain_pack(PTG_DS_OP6_P_F_P_15, PTG_CHAIN_J_ONE, c.time4_p_f_p);
+            else if (c.time45_p_f_p < t && t < c.time5_p_f_p) v = chain_pack(PTG_DS_OP7_P_F_P_22, PTG_CHAIN_J_ONE, c.time5_p_f_p);
+            else v = chain_pack(PTG_DS_OP8_F_P, PTG_CHAIN_J_ONE, 0);
+            chain[(size_t)PTG_CHAIN_P_FROM_OP3 * (top + 1) + t] = v;
+            // _full, part_op == 'op1_start_p' (:703-713)
+            v = t < c.time1_start_p_f ? chain_pack(PTG_DS_OP2_START_F, PTG_CHAIN_J_ONE, 0) : chain_pack(PTG_DS_OP3_P_F, PTG_CHAIN_J_ONE, 0);
+            chain[(size_t)PTG_CHAIN_F_FROM_OP1 * (top + 1) + t] = v;
+            // _full, part_op == 'op8_f_p' (:714-749)
+            if (t < c.time1_f_p_f) v = chain_pack(PTG_DS_OP3_P_F, PTG_CHAIN_J_DEVELOPED, 0);
+            else if (c.time1_f_p_f < t && t < c.time_f_p) v = chain_pack(PTG_DS_OP9_F_P_F_5, PTG_CHAIN_J_KEEP, 0);
+            else if (c.time_f_p < t && t < c.time23_f_p_f) v = chain_pack(PTG_DS_OP9_F_P_F_5, PTG_CHAIN_J_ONE, c.time2_f_p_f);
+            else if (c.time23_f_p_f < t && t < c.time34_f_p_f) v = chain_pack(PTG_DS_OP10_F_P_F_10, PTG_CHAIN_J_ONE, c.time3_f_p_f);
+            else if (c.time34_f_p_f < t && t < c.time45_f_p_f) v = chain_pack(PTG_DS_OP11_F_P_F_15, PTG_CHAIN_J_ONE, c.time4_f_p_f);
+            else if (c.time45_f_p_f < t && t < c.time5_f_p_f) v = chain_pack(PTG_DS_OP12_F_P_F_20, PTG_CHAIN_J_ONE, c.time5_f_p_f);
+            else v = chain_pack(PTG_DS_OP3_P_F, PTG_CHAIN_J_ONE, 0);
+            chain[(size_t)PTG_CHAIN_F_FROM_OP8 * (top + 1) + t] = v;
+        }
+        PTG_TRY(h->upload(&P.chain_tab, chain.data(), chain.size()));
+        P.chain_top = top;
+    }
     if (tables->eps_ind) PTG_TRY(h->upload(&P.eps_ind, tables->eps_ind, (size_t)tables->n_eps_ind));
     else P.eps_ind = nullptr;
 

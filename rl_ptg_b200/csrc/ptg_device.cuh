@@ -51,21 +51,45 @@ struct __align__(16) ClockRow {
 };
 
 // --- packed per-env plant state ---------------------------------------------------------------------------------
-// core = {i, j, k, meta};  meta bits: [0,3) Meth_State, 3 hot_cold, 4 standby is standby_up, 5 startup is
-// startup_hot, [6,11) partial table id, [11,16) full table id, [16,19) current_action
-struct Meta {
-    int state, hot_cold, sb_up, su_hot, part_ds, full_ds, cur_action;
+// core = {i, j, k, meta};  meta bits: [0,3) Meth_State | 3 hot_cold | [4,7) current_action | [7,32) "tabs": five
+// 5-bit table ids indexed by state id = the table currently bound to self.standby / cooldown / self.startup /
+// self.partial / self.full (env/ptg_gym_env.py:111-116), so "the table of the current state" is one shift.
+#define PTG_META_TABS_SHIFT 7
+PTG_HD uint32_t meta_tab(uint32_t meta, int state) { return (meta >> (PTG_META_TABS_SHIFT + 5 * state)) & 31u; }
+PTG_HD uint32_t meta_set_tab(uint32_t meta, int state, uint32_t ds) {
+    const int sh = PTG_META_TABS_SHIFT + 5 * state;
+    return (meta & ~(31u << sh)) | (ds << sh);
+}
+struct Meta {     // unpacked view, cold paths only
+    int state, hot_cold, cur_action, standby_ds, startup_ds, part_ds, full_ds;
 };
 PTG_HD Meta meta_unpack(uint32_t m) {
     Meta r;
-    r.state = m & 7; r.hot_cold = (m >> 3) & 1; r.sb_up = (m >> 4) & 1; r.su_hot = (m >> 5) & 1;
-    r.part_ds = (m >> 6) & 31; r.full_ds = (m >> 11) & 31; r.cur_action = (m >> 16) & 7;
+    r.state = m & 7; r.hot_cold = (m >> 3) & 1; r.cur_action = (m >> 4) & 7;
+    r.standby_ds = meta_tab(m, PTG_STANDBY); r.startup_ds = meta_tab(m, PTG_STARTUP);
+    r.part_ds = meta_tab(m, PTG_PARTIAL_LOAD); r.full_ds = meta_tab(m, PTG_FULL_LOAD);
     return r;
 }
 PTG_HD uint32_t meta_pack(const Meta& r) {
-    return (uint32_t)r.state | ((uint32_t)r.hot_cold << 3) | ((uint32_t)r.sb_up << 4) | ((uint32_t)r.su_hot << 5) |
-           ((uint32_t)r.part_ds << 6) | ((uint32_t)r.full_ds << 11) | ((uint32_t)r.cur_action << 16);
+    uint32_t m = (uint32_t)r.state | ((uint32_t)r.hot_cold << 3) | ((uint32_t)r.cur_action << 4);
+    m = meta_set_tab(m, PTG_STANDBY, r.standby_ds);
+    m = meta_set_tab(m, PTG_COOLDOWN, PTG_DS_COOLDOWN);
+    m = meta_set_tab(m, PTG_STARTUP, r.startup_ds);
+    m = meta_set_tab(m, PTG_PARTIAL_LOAD, r.part_ds);
+    return meta_set_tab(m, PTG_FULL_LOAD, r.full_ds);
 }
+
+// load-change chains of _partial / _full (:636-688, :702-754) as look-up tables over time_op, built on the host
+// from the config thresholds: entry = table id | i/j rule | new i
+#define PTG_CHAIN_P_FROM_OP2F 0      // _partial after op2_start_f
+#define PTG_CHAIN_P_FROM_OP3 1       // _partial after op3_p_f
+#define PTG_CHAIN_F_FROM_OP1 2       // _full after op1_start_p
+#define PTG_CHAIN_F_FROM_OP8 3       // _full after op8_f_p
+#define PTG_CHAIN_J_ONE 0u           // i := new i, j := 1
+#define PTG_CHAIN_J_KEEP 1u          // i kept, j += 1            (:658, :724)
+#define PTG_CHAIN_J_DEVELOPED 2u     // i, j := i/j_fully_developed (:652-653, :718-719)
+#define PTG_CHAIN_J_ARGMIN 3u        // i := argmin(op1_start_p, T_cat), j := 1 (:641-642)
+PTG_HD uint32_t chain_pack(uint32_t ds, uint32_t rule, uint32_t new_i) { return (ds << 27) | (rule << 25) | (new_i & 0x1ffffffu); }
 
 // Scalars of the reward model, shared by the table-build kernel and the eval-mode info path.
 struct RewardConsts {
@@ -108,6 +132,8 @@ struct DevParams {
     const DayRow* day_tab;         // [n_days]
     const ClockRow* clock_tab;     // [eps_sim_steps + 1]
     const int64_t* eps_ind;        // [n_eps_ind] or nullptr
+    const uint32_t* chain_tab;     // [4][chain_top + 1] chain_pack() entries
+    int32_t chain_top;             // time_op values >= chain_top share the last entry
     const double* pot0;            // e_r_b[1, 0, :] fp64 (info "Pot_Reward")
     const double* pf0;             // e_r_b[2, 0, :] fp64 (info "Part_Full")
     ZigTables zig;
@@ -117,11 +143,7 @@ struct DevParams {
     int32_t reset_i, reset_tinfo;
     float reset_norm[6];
     double reset_flow[5];
-    // thresholds
-    int32_t time1_start_p_f, time2_start_f_p, time_p_f, time_f_p;
-    int32_t time1_p_f_p, time2_p_f_p, time3_p_f_p, time34_p_f_p, time4_p_f_p, time45_p_f_p, time5_p_f_p;
-    int32_t time1_f_p_f, time2_f_p_f, time23_f_p_f, time3_f_p_f, time34_f_p_f, time4_f_p_f, time45_f_p_f,
-            time5_f_p_f;
+    // thresholds (the load-change chains live in chain_tab)
     int32_t i_fully_developed, j_fully_developed;
     // scalars
     double noise, eps_len_d, penalty /* r_0 * state_change_penalty */;
@@ -171,16 +193,6 @@ struct RewardParts {
 };
 
 #if defined(__CUDACC__)
-
-__device__ __forceinline__ int cur_table(const Meta& m) {
-    switch (m.state) {
-        case PTG_STANDBY: return m.sb_up ? PTG_DS_STANDBY_UP : PTG_DS_STANDBY_DOWN;
-        case PTG_COOLDOWN: return PTG_DS_COOLDOWN;
-        case PTG_STARTUP: return m.su_hot ? PTG_DS_STARTUP_HOT : PTG_DS_STARTUP_COLD;
-        case PTG_PARTIAL_LOAD: return m.part_ds;
-        default: return m.full_ds;
-    }
-}
 
 // One draw of np_random.normal(0, noise, size=1)[0].  Out of line on purpose: only transitions into
 // standby/cooldown/startup draw, and the 128-bit PCG64 arithmetic would otherwise inflate the register
@@ -258,26 +270,6 @@ __device__ __forceinline__ void reward_coefficients(const RewardConsts& P, const
     c_0 = (u.chp_rev + u.steam_rev + u.o2_rev - u.water_cost) * scale;
 }
 
-// Decode the action of env e (discrete id, or continuous Box(-1,1) -> 5 bins, :346-355)
-__device__ __forceinline__ int decode_action(const DevParams& P, const void* actions, int dtype, int64_t idx,
-                                             int prev_action) {
-    if (!P.continuous) {
-        long long a;
-        if (dtype == PTG_ACT_I64) a = ((const long long*)actions)[idx];
-        else if (dtype == PTG_ACT_I32) a = ((const int*)actions)[idx];
-        else if (dtype == PTG_ACT_U8) a = ((const unsigned char*)actions)[idx];
-        else a = (long long)((const float*)actions)[idx];
-        if (a < 0 || a > 4) { atomicOr(P.err, PTG_EBIT_ACTION); a = PTG_COOLDOWN; }
-        return (int)a;
-    }
-    double a = (double)((const float*)actions)[idx];
-    int act = prev_action;                        // a >= 1.0: no interval matches, previous action is kept
-#pragma unroll
-    for (int ival = 5; ival >= 0; --ival)
-        if (P.prob_thre[ival] > a) act = (ival + 4) % 5;   // first matching ival wins (descending scan)
-    return act;
-}
-
 // episode schedule: which eps_ind entry does env (global id) use for its m-th constructor/reset
 __device__ __forceinline__ void episode_offsets(const DevParams& P, int64_t e, int32_t m, int& ep_h, int& ep_d) {
     if (P.eps_ind == nullptr) { ep_h = 0; ep_d = 0; return; }     // val/test env, :63-64
@@ -289,90 +281,86 @@ __device__ __forceinline__ void episode_offsets(const DevParams& P, int64_t e, i
     ep_d = (int)(v * P.eps_len_d);                // :61 / :492
 }
 
-// Which argmin-LUT column (if any) the coming transition will read: known as soon as (action, state, T flags) are,
-// so the LUT gather and the RNG-state prefetch can be issued before the branchy transition code runs.
-//   return: column 0..5, or -1 when no _get_index is evaluated;  draws = 1 when the transition draws noise
-__device__ __forceinline__ int argmin_column(int action, const Meta& m, int tflags, int& draws) {
-    const int hot = (tflags & PTG_TF_COLD) ? 0 : (tflags & PTG_TF_HOT) ? 1 : m.hot_cold;     // :339-342
-    draws = 0;
-    if (action == PTG_STANDBY && m.state != PTG_STANDBY) { draws = 1; return (tflags & PTG_TF_SBUP) ? 1 : 2; }
-    if (action == PTG_COOLDOWN && m.state != PTG_COOLDOWN) { draws = 1; return 0; }
-    if (action == PTG_STARTUP && m.state < PTG_STARTUP) { draws = 1; return hot ? 4 : 3; }
-    if (action == PTG_PARTIAL_LOAD && m.state == PTG_FULL_LOAD && m.full_ds == PTG_DS_OP2_START_F) return 5;
-    return -1;
+// ---- plant transition, PTGEnv.step (:336-440) + _perform_sim_step (:525-557) ----------------------------------
+// Split in two so that the memory the transition needs can be requested long before the branchy part runs:
+//   plan_transition   : from (action, packed state, T flags) alone -> which handler runs, which table it binds,
+//                       which argmin-LUT column it reads, whether it draws noise
+//   apply_transition  : consumes the LUT value / noise draw -> new (i, j, meta) and the step-table entry
+#define PTG_KIND_CONT 0      // _cont            (:559-570)
+#define PTG_KIND_DRAW 1      // _standby / _cooldown / _startup (:572-625): argmin + noise
+#define PTG_KIND_PARTIAL 2   // _partial         (:627-691)
+#define PTG_KIND_FULL 3      // _full            (:693-756)
+struct Plan {
+    int kind, ds, col;       // col = argmin-LUT column or -1
+};
+
+__device__ __forceinline__ Plan plan_transition(int action, uint32_t& meta, int tflags) {
+    // hot/cold hysteresis (:339-342) and current_action (:347) are updated first, like the reference does
+    uint32_t hot = (tflags & PTG_TF_COLD) ? 0u : (tflags & PTG_TF_HOT) ? 1u : ((meta >> 3) & 1u);
+    meta = (meta & ~(0xfu << 3)) | (hot << 3) | ((uint32_t)action << 4);
+    const int state = meta & 7;
+    // the 5x5 match (:368-440): bit (5*action + state) set <=> the step continues the current table
+    const uint32_t CONT = (1u << 0) | (1u << 6) | (7u << 12) | (15u << 15) | (7u << 20) | (1u << 24);
+    Plan p;
+    p.col = -1;
+    if ((CONT >> (5 * action + state)) & 1u) {
+        p.kind = PTG_KIND_CONT;
+        p.ds = meta_tab(meta, state);
+    } else if (action <= PTG_STARTUP) {
+        p.kind = PTG_KIND_DRAW;
+        p.ds = action == PTG_STANDBY ? ((tflags & PTG_TF_SBUP) ? PTG_DS_STANDBY_UP : PTG_DS_STANDBY_DOWN)      // :579-582
+             : action == PTG_COOLDOWN ? PTG_DS_COOLDOWN
+                                      : (hot ? PTG_DS_STARTUP_HOT : PTG_DS_STARTUP_COLD);                     // :616-619
+        // LUT column of table id 0..5: startup_cold 3, startup_hot 4, cooldown 0, standby_down 2, standby_up 1, op1 5
+        p.col = (0x512043 >> (4 * p.ds)) & 15;
+    } else if (action == PTG_PARTIAL_LOAD) {
+        p.kind = PTG_KIND_PARTIAL;
+        p.ds = 0;
+        if (meta_tab(meta, PTG_FULL_LOAD) == PTG_DS_OP2_START_F) p.col = 5;      // may need argmin(op1_start_p), :641
+    } else {
+        p.kind = PTG_KIND_FULL;
+        p.ds = 0;
+    }
+    return p;
 }
 
-// The plant transition of PTGEnv.step (:336-440 + _perform_sim_step) -> new (core, tinfo) and the step-table
-// entry index that holds this step's window statistics.  `lut_val` = argmin_lut[vid][argmin_column(...)].
-__device__ __forceinline__ int plant_transition(const DevParams& P, int64_t e, int action, int& i, int& j, Meta& m,
-                                                int32_t tinfo_in, int lut_val) {
-    const int tflags = tinfo_in & 7;
-    if (tflags & PTG_TF_COLD) m.hot_cold = 0;          // :339-342
-    else if (tflags & PTG_TF_HOT) m.hot_cold = 1;
-    m.cur_action = action;
+__device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, const Plan& p, int& i, int& j,
+                                                uint32_t& meta, int lut_val) {
     const int S = P.S;
-    int state = m.state, ds, next_state, change = 0;
-    bool cont;
-    switch (action) {                                   // the 5x5 match, :368-440
-        case PTG_STANDBY: cont = (state == PTG_STANDBY); break;
-        case PTG_COOLDOWN: cont = (state == PTG_COOLDOWN); break;
-        case PTG_STARTUP: cont = (state >= PTG_STARTUP); break;
-        case PTG_PARTIAL_LOAD: cont = (state != PTG_FULL_LOAD); break;
-        default: cont = (state != PTG_PARTIAL_LOAD); break;
-    }
-    if (cont) {                                         // _cont, :559-570
+    int state = meta & 7, ds = p.ds, next_state, change = 0;
+    if (p.kind == PTG_KIND_CONT) {
         j += 1;
-        ds = cur_table(m);
-        next_state = (state == PTG_STARTUP) ? PTG_PARTIAL_LOAD : state;
+        next_state = (state == PTG_STARTUP) ? PTG_PARTIAL_LOAD : state;          // :386-388
         change = (state == PTG_STARTUP);
-    } else if (action <= PTG_STARTUP) {                 // _standby / _cooldown / _startup, :572-625
-        if (action == PTG_STANDBY) {
-            m.sb_up = (tflags & PTG_TF_SBUP) ? 1 : 0;
-            ds = m.sb_up ? PTG_DS_STANDBY_UP : PTG_DS_STANDBY_DOWN;
-            next_state = PTG_STANDBY;
-        } else if (action == PTG_COOLDOWN) {
-            ds = PTG_DS_COOLDOWN; next_state = PTG_COOLDOWN;
-        } else {
-            m.part_ds = PTG_DS_OP1_START_P; m.full_ds = PTG_DS_OP2_START_F;
-            m.su_hot = m.hot_cold;
-            ds = m.su_hot ? PTG_DS_STARTUP_HOT : PTG_DS_STARTUP_COLD;
+    } else if (p.kind == PTG_KIND_DRAW) {
+        state = (meta >> 4) & 7;                                                 // new state = action
+        if (state == PTG_STARTUP) {                                              // :611-614
+            meta = meta_set_tab(meta_set_tab(meta, PTG_PARTIAL_LOAD, PTG_DS_OP1_START_P), PTG_FULL_LOAD, PTG_DS_OP2_START_F);
             next_state = PTG_PARTIAL_LOAD; change = 1;
+        } else {
+            next_state = state;
         }
-        state = action;
+        meta = meta_set_tab(meta, state, ds);
         i = jitter_index(lut_val, draw_noise(P, e));
         j = 1;
-    } else if (action == PTG_PARTIAL_LOAD) {            // _partial, :627-691
-        state = PTG_PARTIAL_LOAD; next_state = PTG_PARTIAL_LOAD;
-        const int time_op = i + j * S;
-        int nds = PTG_DS_OP8_F_P, ni = 0, nj = 1;
-        if (m.full_ds == PTG_DS_OP2_START_F) {
-            if (time_op < P.time2_start_f_p) { nds = PTG_DS_OP1_START_P; ni = lut_val; }
-        } else if (m.full_ds == PTG_DS_OP3_P_F) {
-            if (time_op < P.time1_p_f_p) { ni = P.i_fully_developed; nj = P.j_fully_developed; }
-            else if (P.time1_p_f_p < time_op && time_op < P.time2_p_f_p) { nds = PTG_DS_OP4_P_F_P_5; ni = i; nj = j + 1; }
-            else if (P.time2_p_f_p < time_op && time_op < P.time_p_f) { nds = PTG_DS_OP4_P_F_P_5; ni = P.time2_p_f_p; }
-            else if (P.time_p_f < time_op && time_op < P.time34_p_f_p) { nds = PTG_DS_OP5_P_F_P_10; ni = P.time3_p_f_p; }
-            else if (P.time34_p_f_p < time_op && time_op < P.time45_p_f_p) { nds = PTG_DS_OP6_P_F_P_15; ni = P.time4_p_f_p; }
-            else if (P.time45_p_f_p < time_op && time_op < P.time5_p_f_p) { nds = PTG_DS_OP7_P_F_P_22; ni = P.time5_p_f_p; }
-        }
-        m.part_ds = nds; ds = nds; i = ni; j = nj;
-    } else {                                            // _full, :693-756
-        state = PTG_FULL_LOAD; next_state = PTG_FULL_LOAD;
-        const int time_op = i + j * S;
-        int nds = PTG_DS_OP3_P_F, ni = 0, nj = 1;
-        if (m.part_ds == PTG_DS_OP1_START_P) {
-            if (time_op < P.time1_start_p_f) nds = PTG_DS_OP2_START_F;
-        } else if (m.part_ds == PTG_DS_OP8_F_P) {
-            if (time_op < P.time1_f_p_f) { ni = P.i_fully_developed; nj = P.j_fully_developed; }
-            else if (P.time1_f_p_f < time_op && time_op < P.time_f_p) { nds = PTG_DS_OP9_F_P_F_5; ni = i; nj = j + 1; }
-            else if (P.time_f_p < time_op && time_op < P.time23_f_p_f) { nds = PTG_DS_OP9_F_P_F_5; ni = P.time2_f_p_f; }
-            else if (P.time23_f_p_f < time_op && time_op < P.time34_f_p_f) { nds = PTG_DS_OP10_F_P_F_10; ni = P.time3_f_p_f; }
-            else if (P.time34_f_p_f < time_op && time_op < P.time45_f_p_f) { nds = PTG_DS_OP11_F_P_F_15; ni = P.time4_f_p_f; }
-            else if (P.time45_f_p_f < time_op && time_op < P.time5_f_p_f) { nds = PTG_DS_OP12_F_P_F_20; ni = P.time5_f_p_f; }
-        }
-        m.full_ds = nds; ds = nds; i = ni; j = nj;
+    } else {                                                                     // _partial / _full
+        const bool to_partial = p.kind == PTG_KIND_PARTIAL;
+        state = next_state = to_partial ? PTG_PARTIAL_LOAD : PTG_FULL_LOAD;
+        const uint32_t src = meta_tab(meta, to_partial ? PTG_FULL_LOAD : PTG_PARTIAL_LOAD);
+        int chain = -1;
+        if (to_partial) chain = src == PTG_DS_OP2_START_F ? PTG_CHAIN_P_FROM_OP2F : src == PTG_DS_OP3_P_F ? PTG_CHAIN_P_FROM_OP3 : -1;
+        else chain = src == PTG_DS_OP1_START_P ? PTG_CHAIN_F_FROM_OP1 : src == PTG_DS_OP8_F_P ? PTG_CHAIN_F_FROM_OP8 : -1;
+        uint32_t c = chain_pack(to_partial ? PTG_DS_OP8_F_P : PTG_DS_OP3_P_F, PTG_CHAIN_J_ONE, 0);   // :684-688, :750-754
+        if (chain >= 0) c = __ldg(P.chain_tab + chain * (P.chain_top + 1) + min(i + j * S, P.chain_top));
+        ds = c >> 27;
+        const uint32_t rule = (c >> 25) & 3u;
+        const int new_i = (int)(c & 0x1ffffffu);
+        if (rule == PTG_CHAIN_J_KEEP) { j += 1; }
+        else if (rule == PTG_CHAIN_J_DEVELOPED) { i = P.i_fully_developed; j = P.j_fully_developed; }
+        else { i = rule == PTG_CHAIN_J_ARGMIN ? lut_val : new_i; j = 1; }
+        meta = meta_set_tab(meta, state, ds);
     }
-    // _perform_sim_step, :525-557, reduced to index arithmetic: the window [pos-S, pos) clipped/padded at L is
+    // _perform_sim_step (:525-557) reduced to index arithmetic: the window [pos-S, pos) clipped/padded at L is
     // entry min(pos - S, L) of table ds (built by k_build_step_tab with the same padding / hand-over rules)
     const int L = P.ds_len[ds];
     const long long pos = (long long)i + (long long)j * S;
@@ -385,7 +373,7 @@ __device__ __forceinline__ int plant_transition(const DevParams& P, int64_t e, i
             start = L;              // S copies of the last row; (i, j) unchanged
         }
     }
-    m.state = state;
+    meta = (meta & ~7u) | (uint32_t)state;
     return P.ent_off[ds] + (int)start;
 }
 

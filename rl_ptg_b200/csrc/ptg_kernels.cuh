@@ -408,7 +408,7 @@ __device__ __forceinline__ void env_reset_state(const DevParams& P, int64_t e, i
     int ep_h, ep_d;
     episode_offsets(P, e, m_count, ep_h, ep_d);
     ep = make_int2(ep_h, ep_d);
-    m.state = PTG_COOLDOWN; m.hot_cold = 0; m.sb_up = 0; m.su_hot = 0;
+    m.state = PTG_COOLDOWN; m.hot_cold = 0; m.standby_ds = PTG_DS_STANDBY_DOWN; m.startup_ds = PTG_DS_STARTUP_COLD;
     m.part_ds = PTG_DS_OP1_START_P; m.full_ds = PTG_DS_OP2_START_F;
     // current_action is NOT touched by reset() (only by __init__, :143)
     core = make_int4(P.reset_i, 0, 0, (int)meta_pack(m));
@@ -573,13 +573,12 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
     int done = 0, t_hour_out = 0;
     if (active) {
         // (1) what the transition will need from memory
-        Meta m = meta_unpack(meta);
-        const int action = decode_action_raw(P, action_raw, adtype, m.cur_action);
-        int will_draw;
-        const int col = argmin_column(action, m, tinfo & 7, will_draw);
+        const int action = decode_action_raw(P, action_raw, adtype, (meta >> 4) & 7);
+        const int prev_state = meta & 7;
+        const Plan plan = plan_transition(action, meta, tinfo & 7);
         int lut_val = 0;
-        if (col >= 0) lut_val = __ldg(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + col);
-        if (will_draw && P.noise_mode != PTG_NOISE_OFF) prefetch_l1(P.rng + e);
+        if (plan.col >= 0) lut_val = __ldg(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + plan.col);
+        if (plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF) prefetch_l1(P.rng + e);
         // (2) clock row of step k+1 -> market rows of the NEW hour/day (:442-447) -> observation windows
         const int4 c4 = __ldg(reinterpret_cast<const int4*>(P.clock_tab + (k + 1)));
         int t_hour = ep.x + c4.z, t_day = ep.y + c4.w;
@@ -589,14 +588,8 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
         const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
         // (3) plant transition -> step-table entry (4 x 16 B = two sectors)
-        const int prev_state = m.state;
-#if defined(PTG_EXP_NO_TRANSITION)
-        j += 1; const int ent = P.ent_off[PTG_DS_COOLDOWN] + ((i + j + action) & 0x7fff); (void)lut_val;
-#else
-        const int ent = plant_transition(P, e, action, i, j, m, tinfo, lut_val);
-#endif
-        meta = meta_pack(m);
-        const int state_change = (prev_state != m.state);
+        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val);
+        const int state_change = (prev_state != (int)(meta & 7));
         const int4* ep4 = reinterpret_cast<const int4*>(P.step_tab + ent);
         const int4 q0 = __ldg(ep4), q1 = __ldg(ep4 + 1), q2 = __ldg(ep4 + 2), q3 = __ldg(ep4 + 3);
         // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
@@ -609,7 +602,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         o.norm[0] = __int_as_float(q2.x); o.norm[1] = __int_as_float(q2.y); o.norm[2] = __int_as_float(q2.z);
         o.norm[3] = __int_as_float(q2.w); o.norm[4] = __int_as_float(q3.x); o.norm[5] = __int_as_float(q3.y);
         tinfo = q3.z;
-        o.status = m.state;
+        o.status = meta & 7;
         o.sin_h = __int_as_float(c4.x); o.cos_h = __int_as_float(c4.y);
         uint32_t nchg = 0;
         if (P.has_penalty) { nchg = P.nchg[e] + (uint32_t)state_change; P.nchg[e] = nchg; }
@@ -619,7 +612,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
                                                   ep_ret + (double)nchg * P.penalty});
         k += 1;
         if (done) {                                   // SB3 auto-reset (DummyVecEnv.step_wait), out of line
-            finish_episode<NV, MOD>(P, io, e, single, k, ep_ret, m.cur_action, ObsKey{ent, t_hour, t_day, m.state, k});
+            finish_episode<NV, MOD>(P, io, e, single, k, ep_ret, (meta >> 4) & 7, ObsKey{ent, t_hour, t_day, (int)(meta & 7), k});
             const int4 core = P.core[e];              // the reset state written by finish_episode
             tinfo = P.tinfo[e]; ep = P.ep[e];
             i = core.x; j = core.y; k = core.z; meta = (uint32_t)core.w; ep_ret = 0.0;
@@ -785,8 +778,8 @@ __global__ void k_state_unpack(const __grid_constant__ DevParams P, StateDev s, 
     const int4 c = P.core[e];
     const Meta m = meta_unpack((uint32_t)c.w);
     s.meth_state[e] = m.state; s.i[e] = c.x; s.j[e] = c.y; s.k[e] = c.z; s.hot_cold[e] = m.hot_cold;
-    s.standby_ds[e] = m.sb_up ? PTG_DS_STANDBY_UP : PTG_DS_STANDBY_DOWN;
-    s.startup_ds[e] = m.su_hot ? PTG_DS_STARTUP_HOT : PTG_DS_STARTUP_COLD;
+    s.standby_ds[e] = m.standby_ds;
+    s.startup_ds[e] = m.startup_ds;
     s.partial_ds[e] = m.part_ds; s.full_ds[e] = m.full_ds; s.current_action[e] = m.cur_action;
     const int2 ep = P.ep[e];
     s.act_ep_h[e] = ep.x; s.act_ep_d[e] = ep.y; s.episode_count[e] = P.ep_count[e];
@@ -800,7 +793,7 @@ __global__ void k_state_pack(const __grid_constant__ DevParams P, StateDev s, co
     if (e >= P.n_envs) return;
     Meta m;
     m.state = s.meth_state[e]; m.hot_cold = s.hot_cold[e];
-    m.sb_up = (s.standby_ds[e] == PTG_DS_STANDBY_UP); m.su_hot = (s.startup_ds[e] == PTG_DS_STARTUP_HOT);
+    m.standby_ds = s.standby_ds[e]; m.startup_ds = s.startup_ds[e];
     m.part_ds = s.partial_ds[e]; m.full_ds = s.full_ds[e]; m.cur_action = s.current_action[e];
     P.core[e] = make_int4(s.i[e], s.j[e], s.k[e], (int)meta_pack(m));
     P.ep[e] = make_int2(s.act_ep_h[e], s.act_ep_d[e]);
