@@ -325,6 +325,7 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
         PTG_TRY(h->upload(&wi, PTG_ZIG_WI_BITS, 256));
         PTG_TRY(h->upload(&fi, PTG_ZIG_FI_BITS, 256));
         P.zig.ki = ki; P.zig.wi = reinterpret_cast<const double*>(wi); P.zig.fi = reinterpret_cast<const double*>(fi);
+        P.zig.kiwi = nullptr;
     }
 
     PTG_TRY(cudaDeviceSynchronize());

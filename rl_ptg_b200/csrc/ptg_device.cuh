@@ -197,7 +197,7 @@ struct RewardParts {
 // One draw of np_random.normal(0, noise, size=1)[0].  Out of line on purpose: only transitions into
 // standby/cooldown/startup draw, and the 128-bit PCG64 arithmetic would otherwise inflate the register
 // footprint of every thread of the step kernel.
-__device__ __noinline__ double draw_noise(const DevParams& P, int64_t e) {
+__device__ __noinline__ double draw_noise(const DevParams& P, int64_t e, const uint64_t* zig_kiwi) {
     if (P.noise_mode == PTG_NOISE_OFF) return 0.0;
     ulonglong2* rec = reinterpret_cast<ulonglong2*>(P.rng + e);
     const ulonglong2 st = rec[0], dr = rec[1];
@@ -209,7 +209,9 @@ __device__ __noinline__ double draw_noise(const DevParams& P, int64_t e) {
     }
     const ulonglong2 inc = rec[2];
     Pcg64 g = {st.x, st.y, inc.x, inc.y};
-    const double z = pcg64_standard_normal(g, P.zig);
+    ZigTables zt = P.zig;
+    zt.kiwi = zig_kiwi;             // the CTA's shared-memory copy of the hot {ki, wi} pairs
+    const double z = pcg64_standard_normal(g, zt);
     rec[0] = make_ulonglong2(g.s_hi, g.s_lo);
     rec[1] = make_ulonglong2((unsigned long long)(d + 1), 0ull);
     return 0.0 + P.noise * z;      // random_normal: loc + scale * standard_normal
@@ -325,7 +327,7 @@ __device__ __forceinline__ Plan plan_transition(int action, uint32_t& meta, int 
 }
 
 __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, const Plan& p, int& i, int& j,
-                                                uint32_t& meta, int lut_val) {
+                                                uint32_t& meta, int lut_val, const uint64_t* zig_kiwi) {
     const int S = P.S;
     int state = meta & 7, ds = p.ds, next_state, change = 0;
     if (p.kind == PTG_KIND_CONT) {
@@ -341,7 +343,7 @@ __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, c
             next_state = state;
         }
         meta = meta_set_tab(meta, state, ds);
-        i = jitter_index(lut_val, draw_noise(P, e));
+        i = jitter_index(lut_val, draw_noise(P, e, zig_kiwi));
         j = 1;
     } else {                                                                     // _partial / _full
         const bool to_partial = p.kind == PTG_KIND_PARTIAL;

@@ -563,7 +563,7 @@ __device__ __forceinline__ int decode_action_raw(const DevParams& P, long long r
 template <int NV, bool MOD, bool EVAL, int PAC>
 __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, long long action_raw, int adtype,
                                          bool single, int64_t e, bool active, int lane, int64_t warp_env0,
-                                         int nvalid, float* sm, float* __restrict__ obs_out,
+                                         int nvalid, float* sm, const uint64_t* zig_kiwi, float* __restrict__ obs_out,
                                          float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int& i, int& j,
                                          int& k, uint32_t& meta, int32_t& tinfo, int2& ep, double& ep_ret) {
     float4 hrow[NV];
@@ -588,7 +588,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
         const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
         // (3) plant transition -> step-table entry (4 x 16 B = two sectors)
-        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val);
+        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi);
         const int state_change = (prev_state != (int)(meta & 7));
         const int4* ep4 = reinterpret_cast<const int4*>(P.step_tab + ent);
         const int4 q0 = __ldg(ep4), q1 = __ldg(ep4 + 1), q2 = __ldg(ep4 + 2), q3 = __ldg(ep4 + 3);
@@ -655,10 +655,17 @@ __global__ void __launch_bounds__(PTG_BLOCK, PTG_STEP_MIN_BLOCKS)
 k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, int adtype,
        const __grid_constant__ PtgIO io, int T) {
     __shared__ __align__(128) float stage[PTG_BLOCK / 32][2 * PTG_STAGE_FLOATS(NV)];
+    __shared__ __align__(16) uint64_t zig_kiwi[2 * 256];   // {ki, wi} of numpy's ziggurat: 4 KB, one LDS.128 per draw
+    static_assert(PTG_BLOCK == 256, "one ziggurat layer per thread");
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t warp_env0 = e - lane;
-    if (warp_env0 >= P.n_envs) return;                  // whole warp out of range
+    const bool use_zig = P.noise_mode == PTG_NOISE_NUMPY;
+    if (use_zig) {
+        zig_kiwi[2 * threadIdx.x] = __ldg(P.zig.ki + threadIdx.x);
+        zig_kiwi[2 * threadIdx.x + 1] = (uint64_t)__double_as_longlong(__ldg(P.zig.wi + threadIdx.x));
+    }
+    const bool warp_in_range = warp_env0 < P.n_envs;
     const int nvalid = (int)min((int64_t)32, P.n_envs - warp_env0);
     const bool active = e < P.n_envs;
     const int64_t le = active ? e : P.n_envs - 1;       // tail lanes shadow the last env (no stores)
@@ -668,6 +675,8 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     int2 ep = P.ep[le];
     double ep_ret = P.ep_ret[le];
     long long action_raw = load_action_raw(actions, adtype, le);
+    if (use_zig) __syncthreads();                       // ziggurat table visible to every warp of the CTA
+    if (!warp_in_range) return;                         // whole warp out of range
     int i = core.x, j = core.y, k = core.z;
     uint32_t meta = (uint32_t)core.w;
     {   // pull the plant state of the CTA that will run one scheduling wave later into L2 (fire and forget)
@@ -683,12 +692,14 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
 
     if (!MANY) {
         step_one<NV, MOD, EVAL, PAC>(P, io, action_raw, adtype, true, e, active, lane, warp_env0, nvalid, stage[wid],
+                                     use_zig ? zig_kiwi : nullptr,
                                      io.obs, io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
     } else {
         for (int t = 0; t < T; ++t) {
             const long long a_now = action_raw;
             if (t + 1 < T) action_raw = load_action_raw(actions, adtype, (int64_t)(t + 1) * P.n_envs + le);   // next step's
             step_one<NV, MOD, false, PAC>(P, io, a_now, adtype, false, e, active, lane, warp_env0, nvalid, stage[wid],
+                                          use_zig ? zig_kiwi : nullptr,
                                           io.obs + (int64_t)t * P.obs_elems, io.reward + (int64_t)t * P.n_envs,
                                           io.done + (int64_t)t * P.n_envs, i, j, k, meta, tinfo, ep, ep_ret);
         }

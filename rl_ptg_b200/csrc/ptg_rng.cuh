@@ -106,6 +106,7 @@ struct ZigTables {
     const uint64_t* ki;
     const double* wi;
     const double* fi;
+    const uint64_t* kiwi;   // optional interleaved {ki[idx], bits(wi[idx])} pairs (e.g. a shared-memory copy), or null
 };
 
 // numpy random_standard_normal (ziggurat, 256 layers)
@@ -117,9 +118,21 @@ PTG_HD double pcg64_standard_normal(Pcg64& g, const ZigTables& z) {
         r >>= 8;
         int sign = (int)(r & 0x1);
         uint64_t rabs = (r >> 1) & 0x000fffffffffffffull;
-        double x = (double)rabs * z.wi[idx];
+        uint64_t ki;
+        double wi;
+        if (z.kiwi) {
+#if defined(__CUDA_ARCH__)
+            const ulonglong2 kw = reinterpret_cast<const ulonglong2*>(z.kiwi)[idx];
+            ki = kw.x; wi = __longlong_as_double((long long)kw.y);
+#else
+            ki = z.kiwi[2 * idx]; wi = z.wi[idx];
+#endif
+        } else {
+            ki = z.ki[idx]; wi = z.wi[idx];
+        }
+        double x = (double)rabs * wi;
         if (sign) x = -x;
-        if (rabs < z.ki[idx]) return x;   // 99.3 % of draws
+        if (rabs < ki) return x;   // 99.3 % of draws
         if (idx == 0) {
             for (;;) {
                 double xx = -zig_inv_r * log1p(-pcg64_next_double(g));
