@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -116,7 +116,8 @@ def run_reference(args):
     kw = make_kwargs()
     n_envs = 4096 * max(1, cores // 4)
     # each "step" = one lock-step of the bounded sample; keep the whole run within a few minutes
-    rate, dt = cpu_oracle_rate(kw, n_envs, max(1, args.steps), cores, warm=max(1, args.warmup))
+    args.steps = min(args.steps, 300)       # one lock-step of the sample takes ~15 ms; keep the arm within minutes
+    rate, dt = cpu_oracle_rate(kw, n_envs, max(1, args.steps), cores, warm=max(1, min(args.warmup, 5)))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
@@ -178,6 +179,19 @@ def run_gpu(args):
     launches = env.kernel_launches() - l0
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    # secondary: an agent-like "sticky" policy (each env repeats one action; no transition noise after warm-up)
+    sticky = pool[:1].repeat(n_pool, 1).contiguous()
+    for t in range(W):
+        env.step_tensor(sticky[t % n_pool])
+    torch.cuda.synchronize()
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es0.record()
+    for t in range(K):
+        env.step_tensor(sticky[t % n_pool])
+    es1.record()
+    torch.cuda.synchronize()
+    sticky_ms = es0.elapsed_time(es1) / K
+    del sticky
     env.poll_error()
     stats = env.episode_stats(clear=True)       # the path's only collective: one 64-byte all-gather per roll-out
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -248,6 +262,9 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "envs_per_gpu": n_local, "envs_total": n_global,
                        "obs_dim": env.obs_dim, "bytes_per_env_step": bpe, "noise": "on-device PCG64+ziggurat (numpy-exact)",
                        "l2": f"per-step traffic {bpe * n_local / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
+                       "actions": "uniform random over the 5 actions (worst case: ~38% of env-steps redraw noise)",
+                       "sticky_policy_ms_per_step": sticky_ms,
+                       "sticky_policy_roofline_frac": bpe * n_local / (sticky_ms * 1e-3) / 1e9 / peak,
                        "rollout_kernel_ms_per_step": roll_ms, "episodes_finished": stats["episodes"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_step<4,true>",
@@ -267,8 +284,8 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=30)

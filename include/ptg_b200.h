@@ -220,6 +220,11 @@ int64_t ptg_obs_elems(const PtgHandle* h);                       /* fp32 element
 int64_t ptg_num_envs(const PtgHandle* h);
 int64_t ptg_bytes_per_env_step(const PtgHandle* h, int action_dtype);    /* algorithmic HBM bytes, DESIGN.md */
 int ptg_kernel_launches(const PtgHandle* h, int64_t* out);               /* kernels launched by this handle */
+/* Host twins of the on-device generator (no GPU needed): the first n values of
+ * Generator(PCG64(SeedSequence(seed))).standard_normal() -- bit-identical to numpy; used by the CPU test-suite. */
+int ptg_host_standard_normal(uint64_t seed, int64_t n, double* out);
+/* PCG64 state after seeding: out[0..3] = state_hi, state_lo, inc_hi, inc_lo. */
+int ptg_host_seed_state(uint64_t seed, uint64_t* out4);
 const char* ptg_last_error(void);
 int ptg_abi_version(void);
 

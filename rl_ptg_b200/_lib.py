@@ -14,7 +14,8 @@ _LIB = None
 EXPORTS = (
     "ptg_create", "ptg_destroy", "ptg_reset", "ptg_step", "ptg_step_many", "ptg_set_noise_tape", "ptg_get_state",
     "ptg_set_state", "ptg_episode_stats", "ptg_stats_combine", "ptg_poll_error", "ptg_obs_dim", "ptg_obs_layout",
-    "ptg_obs_elems", "ptg_num_envs", "ptg_bytes_per_env_step", "ptg_kernel_launches", "ptg_last_error",
+    "ptg_obs_elems", "ptg_num_envs", "ptg_bytes_per_env_step", "ptg_kernel_launches", "ptg_host_standard_normal",
+    "ptg_host_seed_state", "ptg_last_error",
     "ptg_abi_version",
 )
 
@@ -64,6 +65,8 @@ def load(build_if_missing: bool = False):
     L.ptg_bytes_per_env_step.argtypes = [vp, i32]
     L.ptg_bytes_per_env_step.restype = i64
     L.ptg_kernel_launches.argtypes = [vp, C.POINTER(i64)]
+    L.ptg_host_standard_normal.argtypes = [C.c_uint64, i64, vp]
+    L.ptg_host_seed_state.argtypes = [C.c_uint64, vp]
     L.ptg_last_error.restype = C.c_char_p
     if L.ptg_abi_version() != _abi.PTG_ABI_VERSION:
         raise ImportError("libptg_b200.so ABI version mismatch; rebuild it")

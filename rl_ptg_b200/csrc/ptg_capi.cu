@@ -584,5 +584,21 @@ extern "C" int ptg_kernel_launches(const PtgHandle* h, int64_t* out) {
     return PTG_OK;
 }
 
+extern "C" int ptg_host_standard_normal(uint64_t seed, int64_t n, double* out) {
+    if (!out || n < 0) return fail(PTG_ERR_INVALID_ARGUMENT, "bad output buffer");
+    ZigTables z{PTG_ZIG_KI, reinterpret_cast<const double*>(PTG_ZIG_WI_BITS), reinterpret_cast<const double*>(PTG_ZIG_FI_BITS),
+                nullptr};
+    Pcg64 g = pcg64_from_seed(seed);
+    for (int64_t q = 0; q < n; ++q) out[q] = pcg64_standard_normal(g, z);
+    return PTG_OK;
+}
+
+extern "C" int ptg_host_seed_state(uint64_t seed, uint64_t* out4) {
+    if (!out4) return fail(PTG_ERR_INVALID_ARGUMENT, "null output");
+    const Pcg64 g = pcg64_from_seed(seed);
+    out4[0] = g.s_hi; out4[1] = g.s_lo; out4[2] = g.i_hi; out4[3] = g.i_lo;
+    return PTG_OK;
+}
+
 extern "C" const char* ptg_last_error(void) { return g_last_error.c_str(); }
 extern "C" int ptg_abi_version(void) { return PTG_ABI_VERSION; }

@@ -10,6 +10,7 @@ import numpy as np
 
 import rl_ptg_b200 as ptg
 
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 REF_DATA = os.path.join(GOLDEN_DIR, "ref_data.npz")
 GOLDEN_CASES = sorted(os.path.basename(p)[len("golden_"):-len(".npz")]
