@@ -109,6 +109,23 @@ struct __align__(16) RngRec {
 };
 static_assert(sizeof(RngRec) == 64, "RngRec layout");
 
+#if defined(__CUDACC__)
+// --- 256-bit global accesses (sm_100+: LDG.E.256 / STG.E.256): one instruction and ONE L1 wavefront per lane for a
+//     32 B sector instead of two 128-bit accesses -- the table gathers of the step kernel are wavefront-bound ---
+struct U256 { unsigned long long a, b, c, d; };
+__device__ __forceinline__ U256 ldg256_nc(const void* p) {      // read-only tables (non-coherent path)
+    U256 r;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ U256 ld256(const void* p) {          // read-write data
+    U256 r;
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p) : "memory");
+    return r;
+}
+// (256-bit STORES are deliberately not used: ptxas 12.9 turned `st.global.v4.u64` into a single STG.E.64 here.)
+#endif
+
 // --- everything a kernel needs, passed by value (__grid_constant__) ---------------------------------------------
 struct DevParams {
     // sizes
@@ -199,21 +216,20 @@ struct RewardParts {
 // footprint of every thread of the step kernel.
 __device__ __noinline__ double draw_noise(const DevParams& P, int64_t e, const uint64_t* zig_kiwi) {
     if (P.noise_mode == PTG_NOISE_OFF) return 0.0;
-    ulonglong2* rec = reinterpret_cast<ulonglong2*>(P.rng + e);
-    const ulonglong2 st = rec[0], dr = rec[1];
-    const int64_t d = (int64_t)dr.x;
+    RngRec* rec = P.rng + e;
+    U256 lo = ld256(rec);                           // {state_hi, state_lo, draws, pad}: one 32 B sector
+    const int64_t d = (int64_t)lo.c;
+    rec->draws = d + 1;
     if (P.noise_mode == PTG_NOISE_TAPE) {
-        rec[1] = make_ulonglong2((unsigned long long)(d + 1), 0ull);
         if (d >= P.tape_len) { atomicOr(P.err, PTG_EBIT_TAPE); return 0.0; }
         return P.tape[e * P.tape_len + d];
     }
-    const ulonglong2 inc = rec[2];
-    Pcg64 g = {st.x, st.y, inc.x, inc.y};
+    const ulonglong2 inc = reinterpret_cast<const ulonglong2*>(rec)[2];
+    Pcg64 g = {lo.a, lo.b, inc.x, inc.y};
     ZigTables zt = P.zig;
     zt.kiwi = zig_kiwi;             // the CTA's shared-memory copy of the hot {ki, wi} pairs
     const double z = pcg64_standard_normal(g, zt);
-    rec[0] = make_ulonglong2(g.s_hi, g.s_lo);
-    rec[1] = make_ulonglong2((unsigned long long)(d + 1), 0ull);
+    reinterpret_cast<ulonglong2*>(rec)[0] = make_ulonglong2(g.s_hi, g.s_lo);
     return 0.0 + P.noise * z;      // random_normal: loc + scale * standard_normal
 }
 

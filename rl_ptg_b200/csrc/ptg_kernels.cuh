@@ -330,19 +330,33 @@ __device__ __noinline__ void emit_obs_scalar(const DevParams& P, float* __restri
     sc[8 * P.n_pad] = c.cos_h;
 }
 
+__device__ __forceinline__ float4 f4_lo(unsigned long long a, unsigned long long b) {
+    return make_float4(__uint_as_float((uint32_t)a), __uint_as_float((uint32_t)(a >> 32)), __uint_as_float((uint32_t)b),
+                       __uint_as_float((uint32_t)(b >> 32)));
+}
+
 template <int NV>
 __device__ __forceinline__ void load_hour_row(const DevParams& P, int t_hour, float4 (&hrow)[NV]) {
     const float4* src = P.hour_tab + (int64_t)t_hour * NV;
+    if (NV % 2 == 0) {                      // rows are multiples of 32 B: 256-bit gathers
 #pragma unroll
-    for (int v = 0; v < NV; ++v) hrow[v] = __ldg(src + v);
+        for (int v = 0; v < NV; v += 2) {
+            const U256 r = ldg256_nc(src + v);
+            hrow[v] = f4_lo(r.a, r.b);
+            hrow[v + 1 < NV ? v + 1 : v] = f4_lo(r.c, r.d);
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) hrow[v] = __ldg(src + v);
+    }
 }
 
 __device__ __forceinline__ DayRow load_day_row(const DevParams& P, int t_day) {
-    const int4* src = reinterpret_cast<const int4*>(P.day_tab + t_day);
-    int4 a = __ldg(src), b = __ldg(src + 1);
+    const U256 r = ldg256_nc(P.day_tab + t_day);
     DayRow d;
-    d.gas = __hiloint2double(a.y, a.x); d.eua = __hiloint2double(a.w, a.z);
-    d.gas_n0 = __int_as_float(b.x); d.gas_n1 = __int_as_float(b.y); d.eua_n0 = __int_as_float(b.z); d.eua_n1 = __int_as_float(b.w);
+    d.gas = __longlong_as_double((long long)r.a); d.eua = __longlong_as_double((long long)r.b);
+    d.gas_n0 = __uint_as_float((uint32_t)r.c); d.gas_n1 = __uint_as_float((uint32_t)(r.c >> 32));
+    d.eua_n0 = __uint_as_float((uint32_t)r.d); d.eua_n1 = __uint_as_float((uint32_t)(r.d >> 32));
     return d;
 }
 
@@ -590,18 +604,19 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         // (3) plant transition -> step-table entry (4 x 16 B = two sectors)
         const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi);
         const int state_change = (prev_state != (int)(meta & 7));
-        const int4* ep4 = reinterpret_cast<const int4*>(P.step_tab + ent);
-        const int4 q0 = __ldg(ep4), q1 = __ldg(ep4 + 1), q2 = __ldg(ep4 + 2), q3 = __ldg(ep4 + 3);
+        const U256 qc = ldg256_nc(P.step_tab + ent);                                    // c_gas, c_eua, c_el, c_0
+        const U256 qn = ldg256_nc(reinterpret_cast<const char*>(P.step_tab + ent) + 32);  // norm[6], tinfo, pad
         // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
-        const double c_gas = __hiloint2double(q0.y, q0.x), c_eua = __hiloint2double(q0.w, q0.z);
-        const double c_el = __hiloint2double(q1.y, q1.x), c_0 = __hiloint2double(q1.w, q1.z);
+        const double c_gas = __longlong_as_double((long long)qc.a), c_eua = __longlong_as_double((long long)qc.b);
+        const double c_el = __longlong_as_double((long long)qc.c), c_0 = __longlong_as_double((long long)qc.d);
         double rew = __fma_rn(c_gas, day.gas, __fma_rn(c_eua, day.eua, __fma_rn(-c_el, el, c_0)));
         if (state_change) rew -= P.penalty;
         ep_ret += rew;
         reward = (float)rew;
-        o.norm[0] = __int_as_float(q2.x); o.norm[1] = __int_as_float(q2.y); o.norm[2] = __int_as_float(q2.z);
-        o.norm[3] = __int_as_float(q2.w); o.norm[4] = __int_as_float(q3.x); o.norm[5] = __int_as_float(q3.y);
-        tinfo = q3.z;
+        o.norm[0] = __uint_as_float((uint32_t)qn.a); o.norm[1] = __uint_as_float((uint32_t)(qn.a >> 32));
+        o.norm[2] = __uint_as_float((uint32_t)qn.b); o.norm[3] = __uint_as_float((uint32_t)(qn.b >> 32));
+        o.norm[4] = __uint_as_float((uint32_t)qn.c); o.norm[5] = __uint_as_float((uint32_t)(qn.c >> 32));
+        tinfo = (int32_t)(uint32_t)qn.d;
         o.status = meta & 7;
         o.sin_h = __int_as_float(c4.x); o.cos_h = __int_as_float(c4.y);
         uint32_t nchg = 0;
