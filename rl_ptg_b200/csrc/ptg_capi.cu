@@ -116,6 +116,7 @@ int validate(const PtgConfig* c, const PtgTables* t, int64_t n_envs, int64_t off
         return fail(PTG_ERR_INVALID_ARGUMENT, "sim_step / time_step_op must give at least one row per step");
     if (c->eps_sim_steps < 7) return fail(PTG_ERR_INVALID_ARGUMENT, "eps_sim_steps must be >= 7 (episodes end at eps_sim_steps - 6)");
     if (n_envs < 1 || off < 0 || n_global < off + n_envs) return fail(PTG_ERR_INVALID_ARGUMENT, "bad n_envs / env_id_offset / n_envs_global");
+    if (n_envs > (int64_t)1 << 26) return fail(PTG_ERR_UNSUPPORTED, "more than 2^26 envs per handle (shard across handles / GPUs)");
     const int S = c->sim_step / c->time_step_op;
     int64_t total = 0;
     for (int d = 0; d < PTG_N_DATASETS; ++d) {

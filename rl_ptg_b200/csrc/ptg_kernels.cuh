@@ -257,8 +257,8 @@ __device__ __forceinline__ void stage_windows(const DevParams& P, float* sm, int
 }
 
 template <int NV, bool MOD, int PAC>
-__device__ __forceinline__ void flush_obs(const DevParams& P, float* __restrict__ obs, float* sm, int64_t e,
-                                          bool active, int lane, int64_t warp_env0, int nvalid, const DayRow& day,
+__device__ __forceinline__ void flush_obs(const DevParams& P, float* __restrict__ obs, float* sm, int e,
+                                          bool active, int lane, int warp_env0, int nvalid, const DayRow& day,
                                           const ObsRegs& o) {
     const int pa = PAC > 0 ? PAC : P.pa;
     float* smA = sm;
@@ -294,8 +294,8 @@ __device__ __forceinline__ void flush_obs(const DevParams& P, float* __restrict_
 }
 
 template <int NV, bool MOD>
-__device__ __forceinline__ void emit_obs(const DevParams& P, float* __restrict__ obs, float* sm, int64_t e,
-                                         bool active, int lane, int64_t warp_env0, int nvalid,
+__device__ __forceinline__ void emit_obs(const DevParams& P, float* __restrict__ obs, float* sm, int e,
+                                         bool active, int lane, int warp_env0, int nvalid,
                                          const float4 (&hrow)[NV], const DayRow& day, const ObsRegs& o) {
     stage_windows<NV, MOD, 0>(P, sm, lane, hrow);
     flush_obs<NV, MOD, 0>(P, obs, sm, e, active, lane, warp_env0, nvalid, day, o);
@@ -464,11 +464,11 @@ template <int NV, bool MOD>
 __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ DevParams P, const int64_t* seeds,
                                                      const uint8_t* mask, const __grid_constant__ PtgIO io) {
     __shared__ __align__(128) float stage[PTG_BLOCK / 32][2 * PTG_STAGE_FLOATS(NV)];
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t warp_env0 = e - lane;
-    const int nvalid = (int)min((int64_t)32, P.n_envs - warp_env0);
-    const bool active = e < P.n_envs;
+    const int warp_env0 = e - lane;
+    const int nvalid = min(32, (int)P.n_envs - warp_env0);
+    const bool active = e < (int)P.n_envs;
     const bool doit = active && (mask == nullptr || mask[e]);
     // masked reset: only the selected envs write; the window blocks go through the scalar path then
     float4 hrow[NV];
@@ -576,7 +576,7 @@ __device__ __forceinline__ int decode_action_raw(const DevParams& P, long long r
 //   4. bulk stores
 template <int NV, bool MOD, bool EVAL, int PAC>
 __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, long long action_raw, int adtype,
-                                         bool single, int64_t e, bool active, int lane, int64_t warp_env0,
+                                         bool single, int e, bool active, int lane, int warp_env0,
                                          int nvalid, float* sm, const uint64_t* zig_kiwi, float* __restrict__ obs_out,
                                          float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int& i, int& j,
                                          int& k, uint32_t& meta, int32_t& tinfo, int2& ep, double& ep_ret) {
@@ -672,18 +672,19 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     __shared__ __align__(128) float stage[PTG_BLOCK / 32][2 * PTG_STAGE_FLOATS(NV)];
     __shared__ __align__(16) uint64_t zig_kiwi[2 * 256];   // {ki, wi} of numpy's ziggurat: 4 KB, one LDS.128 per draw
     static_assert(PTG_BLOCK == 256, "one ziggurat layer per thread");
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_envs = (int)P.n_envs;                   // < 2^26 (checked by ptg_create): 32-bit index arithmetic
+    const int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t warp_env0 = e - lane;
+    const int warp_env0 = e - lane;
     const bool use_zig = P.noise_mode == PTG_NOISE_NUMPY;
     if (use_zig) {
         zig_kiwi[2 * threadIdx.x] = __ldg(P.zig.ki + threadIdx.x);
         zig_kiwi[2 * threadIdx.x + 1] = (uint64_t)__double_as_longlong(__ldg(P.zig.wi + threadIdx.x));
     }
-    const bool warp_in_range = warp_env0 < P.n_envs;
-    const int nvalid = (int)min((int64_t)32, P.n_envs - warp_env0);
-    const bool active = e < P.n_envs;
-    const int64_t le = active ? e : P.n_envs - 1;       // tail lanes shadow the last env (no stores)
+    const bool warp_in_range = warp_env0 < n_envs;
+    const int nvalid = min(32, n_envs - warp_env0);
+    const bool active = e < n_envs;
+    const int le = active ? e : n_envs - 1;             // tail lanes shadow the last env (no stores)
 
     const int4 core = P.core[le];
     int32_t tinfo = P.tinfo[le];
@@ -695,13 +696,13 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     int i = core.x, j = core.y, k = core.z;
     uint32_t meta = (uint32_t)core.w;
     {   // pull the plant state of the CTA that will run one scheduling wave later into L2 (fire and forget)
-        const int64_t pe = e + (int64_t)P.prefetch_distance;
-        if (pe < P.n_envs) {
+        const int pe = e + P.prefetch_distance;
+        if (pe < n_envs) {
             prefetch_l2(P.core + pe);
             if ((lane & 3) == 0) prefetch_l2(P.ep_ret + pe);
             if ((lane & 3) == 1) prefetch_l2(P.ep + pe);
             if ((lane & 7) == 2) prefetch_l2(P.tinfo + pe);
-            if (!MANY && (lane & 3) == 3) prefetch_l2(reinterpret_cast<const char*>(actions) + pe * P.action_bytes);
+            if (!MANY && (lane & 3) == 3) prefetch_l2(reinterpret_cast<const char*>(actions) + (int64_t)pe * P.action_bytes);
         }
     }
 
@@ -712,11 +713,11 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     } else {
         for (int t = 0; t < T; ++t) {
             const long long a_now = action_raw;
-            if (t + 1 < T) action_raw = load_action_raw(actions, adtype, (int64_t)(t + 1) * P.n_envs + le);   // next step's
+            if (t + 1 < T) action_raw = load_action_raw(actions, adtype, (int64_t)(t + 1) * n_envs + le);   // next step's
             step_one<NV, MOD, false, PAC>(P, io, a_now, adtype, false, e, active, lane, warp_env0, nvalid, stage[wid],
                                           use_zig ? zig_kiwi : nullptr,
-                                          io.obs + (int64_t)t * P.obs_elems, io.reward + (int64_t)t * P.n_envs,
-                                          io.done + (int64_t)t * P.n_envs, i, j, k, meta, tinfo, ep, ep_ret);
+                                          io.obs + (int64_t)t * P.obs_elems, io.reward + (int64_t)t * n_envs,
+                                          io.done + (int64_t)t * n_envs, i, j, k, meta, tinfo, ep, ep_ret);
         }
     }
     if (active) {
