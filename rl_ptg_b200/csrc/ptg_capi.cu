@@ -114,6 +114,7 @@ int validate(const PtgConfig* c, const PtgTables* t, int64_t n_envs, int64_t off
     if (c->price_ahead > PTG_MAX_PRICE_AHEAD) return fail(PTG_ERR_UNSUPPORTED, "price_ahead > 16 is not supported by the packed hour row");
     if (c->sim_step <= 0 || c->time_step_op <= 0 || c->sim_step / c->time_step_op < 1)
         return fail(PTG_ERR_INVALID_ARGUMENT, "sim_step / time_step_op must give at least one row per step");
+    if ((int64_t)c->eps_sim_steps * c->sim_step > 0x7fffffffLL) return fail(PTG_ERR_UNSUPPORTED, "eps_sim_steps * sim_step must fit 31 bits");
     if (c->eps_sim_steps < 7) return fail(PTG_ERR_INVALID_ARGUMENT, "eps_sim_steps must be >= 7 (episodes end at eps_sim_steps - 6)");
     if (n_envs < 1 || off < 0 || n_global < off + n_envs) return fail(PTG_ERR_INVALID_ARGUMENT, "bad n_envs / env_id_offset / n_envs_global");
     if (n_envs > (int64_t)1 << 26) return fail(PTG_ERR_UNSUPPORTED, "more than 2^26 envs per handle (shard across handles / GPUs)");

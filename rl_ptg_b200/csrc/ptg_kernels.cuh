@@ -256,10 +256,10 @@ __device__ __forceinline__ void stage_windows(const DevParams& P, float* sm, int
     }
 }
 
+// The warp's two staged window tiles leave the SM as one bulk async copy (TMA) each.
 template <int NV, bool MOD, int PAC>
-__device__ __forceinline__ void flush_obs(const DevParams& P, float* __restrict__ obs, float* sm, int e,
-                                          bool active, int lane, int warp_env0, int nvalid, const DayRow& day,
-                                          const ObsRegs& o) {
+__device__ __forceinline__ void issue_window_stores(const DevParams& P, float* __restrict__ obs, float* sm, int lane,
+                                                    int warp_env0, int nvalid) {
     const int pa = PAC > 0 ? PAC : P.pa;
     float* smA = sm;
     float* smB = sm + PTG_STAGE_FLOATS(NV);
@@ -280,7 +280,12 @@ __device__ __forceinline__ void flush_obs(const DevParams& P, float* __restrict_
             if (MOD) gB[idx] = smB[idx];
         }
     }
-    if (!active) return;
+}
+
+// The nine scalar observation keys (+ the raw design's daily price pairs): plain coalesced stores.
+template <bool MOD>
+__device__ __forceinline__ void store_obs_scalars(const DevParams& P, float* __restrict__ obs, int e,
+                                                  const DayRow& day, const ObsRegs& o) {
     if (!MOD) {
         reinterpret_cast<float2*>(obs + P.off_gas)[e] = make_float2(day.gas_n0, day.gas_n1);
         reinterpret_cast<float2*>(obs + P.off_eua)[e] = make_float2(day.eua_n0, day.eua_n1);
@@ -291,6 +296,14 @@ __device__ __forceinline__ void flush_obs(const DevParams& P, float* __restrict_
     for (int q = 0; q < 6; ++q) sc[(1 + q) * P.n_pad] = o.norm[q];
     sc[7 * P.n_pad] = o.sin_h;
     sc[8 * P.n_pad] = o.cos_h;
+}
+
+template <int NV, bool MOD, int PAC>
+__device__ __forceinline__ void flush_obs(const DevParams& P, float* __restrict__ obs, float* sm, int e,
+                                          bool active, int lane, int warp_env0, int nvalid, const DayRow& day,
+                                          const ObsRegs& o) {
+    issue_window_stores<NV, MOD, PAC>(P, obs, sm, lane, warp_env0, nvalid);
+    if (active) store_obs_scalars<MOD>(P, obs, e, day, o);
 }
 
 template <int NV, bool MOD>
@@ -584,7 +597,11 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
     DayRow day;
     ObsRegs o;
     float reward = 0.f;
-    int done = 0, t_hour_out = 0;
+    int t_hour_out = 0;
+    // termination only depends on the step counter (:508-511, k before the increment): known up front, so the
+    // common case (no env of the warp ends its episode) can hand its window tiles to the TMA early
+    const int done = active && (k == P.eps_sim_steps - 6);
+    const bool any_done = __any_sync(0xffffffffu, done);
     if (active) {
         // (1) what the transition will need from memory
         const int action = decode_action_raw(P, action_raw, adtype, (meta >> 4) & 7);
@@ -593,19 +610,23 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         int lut_val = 0;
         if (plan.col >= 0) lut_val = __ldg(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + plan.col);
         if (plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF) prefetch_l1(P.rng + e);
-        // (2) clock row of step k+1 -> market rows of the NEW hour/day (:442-447) -> observation windows
-        const int4 c4 = __ldg(reinterpret_cast<const int4*>(P.clock_tab + (k + 1)));
-        int t_hour = ep.x + c4.z, t_day = ep.y + c4.w;
+        // (2) clock of step k+1 (:442-445, integer form of floor(clock_hours), floor(clock_days)) -> market rows of
+        //     the NEW hour/day (:446-447) -> observation windows; sin/cos of the clock come from the clock table
+        const unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
+        int t_hour = ep.x + (int)(sec / 3600u), t_day = ep.y + (int)(sec / 86400u);
         clamp_market_index(P, t_hour, t_day);
         load_hour_row<NV>(P, t_hour, hrow);
         day = load_day_row(P, t_day);
+        const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + (k + 1)));
         stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
         const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
-        // (3) plant transition -> step-table entry (4 x 16 B = two sectors)
+        // (3) plant transition -> step-table entry (2 x 32 B = two sectors)
         const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi);
         const int state_change = (prev_state != (int)(meta & 7));
         const U256 qc = ldg256_nc(P.step_tab + ent);                                    // c_gas, c_eua, c_el, c_0
         const U256 qn = ldg256_nc(reinterpret_cast<const char*>(P.step_tab + ent) + 32);  // norm[6], tinfo, pad
+        // (4) window tiles -> TMA while the gather above is in flight (the warp reconverges here)
+        if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
         // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
         const double c_gas = __longlong_as_double((long long)qc.a), c_eua = __longlong_as_double((long long)qc.b);
         const double c_el = __longlong_as_double((long long)qc.c), c_0 = __longlong_as_double((long long)qc.d);
@@ -618,10 +639,9 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         o.norm[4] = __uint_as_float((uint32_t)qn.c); o.norm[5] = __uint_as_float((uint32_t)(qn.c >> 32));
         tinfo = (int32_t)(uint32_t)qn.d;
         o.status = meta & 7;
-        o.sin_h = __int_as_float(c4.x); o.cos_h = __int_as_float(c4.y);
+        o.sin_h = sc2.x; o.cos_h = sc2.y;
         uint32_t nchg = 0;
         if (P.has_penalty) { nchg = P.nchg[e] + (uint32_t)state_change; P.nchg[e] = nchg; }
-        done = (k == P.eps_sim_steps - 6);            // :508-511 (k before the increment)
         if (EVAL && io.info != nullptr)
             write_info<NV>(P, io.info, e, InfoKey{k, t_hour, t_day, ent, state_change, meta, rew,
                                                   ep_ret + (double)nchg * P.penalty});
@@ -646,18 +666,20 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         day = DayRow{};
         o = ObsRegs{};
         stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
+        if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
     }
     // episode ends are rare: only then is the warp's window tile staged again, from re-read hour rows (the reset
-    // observation of the done lanes, the unchanged rows of the others)
-    if (__any_sync(0xffffffffu, done)) {
+    // observation of the done lanes, the unchanged rows of the others), and stored after the fact
+    if (any_done) {
         float4 h2[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) h2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) load_hour_row<NV>(P, t_hour_out, h2);
         stage_windows<NV, MOD, PAC>(P, sm, lane, h2);
+        issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
     }
-    flush_obs<NV, MOD, PAC>(P, obs_out, sm, e, active, lane, warp_env0, nvalid, day, o);
     if (active) {
+        store_obs_scalars<MOD>(P, obs_out, e, day, o);
         rew_out[e] = reward;
         done_out[e] = (uint8_t)done;
     }
