@@ -112,11 +112,43 @@ static_assert(sizeof(RngRec) == 64, "RngRec layout");
 #if defined(__CUDACC__)
 // --- 256-bit global accesses (sm_100+: LDG.E.256 / STG.E.256): one instruction and ONE L1 wavefront per lane for a
 //     32 B sector instead of two 128-bit accesses -- the table gathers of the step kernel are wavefront-bound ---
+// L2 residency: one step streams ~250 MB of per-env state and observations through the 126 MB L2, which evicts the
+// (16 MB of) tables unless the table gathers ask for evict_last and the streaming stores for evict_first.  The
+// policy words are what `createpolicy.fractional.L2::evict_{last,first}.b64 p, 1.0` returns (as immediates they
+// cost no live registers).
+#ifndef PTG_L2_HINTS
+#define PTG_L2_HINTS 1
+#endif
+#define PTG_L2_EVICT_FIRST 0x12F0000000000000ull
+#define PTG_L2_EVICT_LAST 0x14F0000000000000ull
 struct U256 { unsigned long long a, b, c, d; };
 __device__ __forceinline__ U256 ldg256_nc(const void* p) {      // read-only tables (non-coherent path)
     U256 r;
+#if PTG_L2_HINTS
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p), "l"(PTG_L2_EVICT_LAST));
+#else
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
+#endif
     return r;
+}
+__device__ __forceinline__ int ldg32_nc_keep(const int* p) {     // small read-only tables (argmin LUT)
+#if PTG_L2_HINTS
+    int r;
+    asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(PTG_L2_EVICT_LAST));
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
+// streaming stores (written once per step, re-read one full step later at the earliest)
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, T v) {
+#if PTG_L2_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
 }
 __device__ __forceinline__ U256 ld256(const void* p) {          // read-write data
     U256 r;
@@ -211,20 +243,33 @@ struct RewardParts {
 
 #if defined(__CUDACC__)
 
+// The RNG record of a drawing lane: both 32 B sectors are requested back to back (sector 0 = state + draw counter,
+// read-modify-written; sector 1 = the constant increment, non-coherent path), then consumed by draw_noise.
+struct RngLoad {
+    U256 lo;            // {s_hi, s_lo, draws, pad}
+    ulonglong2 inc;     // {i_hi, i_lo}
+};
+__device__ __forceinline__ RngLoad request_rng(const DevParams& P, int64_t e) {
+    const RngRec* rec = P.rng + e;
+    RngLoad r;
+    r.inc = make_ulonglong2(0, 0);
+    if (P.noise_mode == PTG_NOISE_NUMPY)
+        asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(r.inc.x), "=l"(r.inc.y) : "l"(reinterpret_cast<const char*>(rec) + 32));
+    r.lo = ld256(rec);
+    return r;
+}
+
 // One draw of np_random.normal(0, noise, size=1)[0].  (Measured: inlining beats an out-of-line call here -- the
 // call's register save/restore costs more than the 128-bit PCG64 arithmetic adds to the live set.)
-__device__ __forceinline__ double draw_noise(const DevParams& P, int64_t e, const uint64_t* zig_kiwi) {
-    if (P.noise_mode == PTG_NOISE_OFF) return 0.0;
+__device__ __forceinline__ double draw_noise(const DevParams& P, int64_t e, const uint64_t* zig_kiwi, const RngLoad& r) {
     RngRec* rec = P.rng + e;
-    U256 lo = ld256(rec);                           // {state_hi, state_lo, draws, pad}: one 32 B sector
-    const int64_t d = (int64_t)lo.c;
+    const int64_t d = (int64_t)r.lo.c;
     rec->draws = d + 1;
     if (P.noise_mode == PTG_NOISE_TAPE) {
         if (d >= P.tape_len) { atomicOr(P.err, PTG_EBIT_TAPE); return 0.0; }
         return P.tape[e * P.tape_len + d];
     }
-    const ulonglong2 inc = reinterpret_cast<const ulonglong2*>(rec)[2];
-    Pcg64 g = {lo.a, lo.b, inc.x, inc.y};
+    Pcg64 g = {r.lo.a, r.lo.b, r.inc.x, r.inc.y};
     ZigTables zt = P.zig;
     zt.kiwi = zig_kiwi;             // the CTA's shared-memory copy of the hot {ki, wi} pairs
     const double z = pcg64_standard_normal(g, zt);
@@ -341,8 +386,11 @@ __device__ __forceinline__ Plan plan_transition(int action, uint32_t& meta, int 
     return p;
 }
 
+// EARLY: the RNG record was requested by the caller right after plan_transition (rl); otherwise it is requested here
+template <bool EARLY>
 __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, const Plan& p, int& i, int& j,
-                                                uint32_t& meta, int lut_val, const uint64_t* zig_kiwi) {
+                                                uint32_t& meta, int lut_val, const uint64_t* zig_kiwi,
+                                                const RngLoad& rl) {
     const int S = P.S;
     int state = meta & 7, ds = p.ds, next_state, change = 0;
     if (p.kind == PTG_KIND_CONT) {
@@ -358,7 +406,9 @@ __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, c
             next_state = state;
         }
         meta = meta_set_tab(meta, state, ds);
-        i = jitter_index(lut_val, draw_noise(P, e, zig_kiwi));
+        double nz = 0.0;
+        if (P.noise_mode != PTG_NOISE_OFF) nz = EARLY ? draw_noise(P, e, zig_kiwi, rl) : draw_noise(P, e, zig_kiwi, request_rng(P, e));
+        i = jitter_index(lut_val, nz);
         j = 1;
     } else {                                                                     // _partial / _full
         const bool to_partial = p.kind == PTG_KIND_PARTIAL;

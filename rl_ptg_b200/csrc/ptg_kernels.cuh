@@ -220,8 +220,13 @@ struct ObsRegs {            // what one env contributes to the observation, in r
 // --- TMA (bulk async copy) helpers: shared::cta -> global, 1-D ---------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+#if PTG_L2_HINTS
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes), "l"(PTG_L2_EVICT_FIRST) : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores of this thread have finished READING shared memory (the staging buffer may be rewritten)
@@ -287,15 +292,15 @@ template <bool MOD>
 __device__ __forceinline__ void store_obs_scalars(const DevParams& P, float* __restrict__ obs, int e,
                                                   const DayRow& day, const ObsRegs& o) {
     if (!MOD) {
-        reinterpret_cast<float2*>(obs + P.off_gas)[e] = make_float2(day.gas_n0, day.gas_n1);
-        reinterpret_cast<float2*>(obs + P.off_eua)[e] = make_float2(day.eua_n0, day.eua_n1);
+        st_stream(reinterpret_cast<float2*>(obs + P.off_gas) + e, make_float2(day.gas_n0, day.gas_n1));
+        st_stream(reinterpret_cast<float2*>(obs + P.off_eua) + e, make_float2(day.eua_n0, day.eua_n1));
     }
     float* sc = obs + P.off_scalar + e;
-    sc[0] = __int_as_float(o.status);
+    st_stream(sc, __int_as_float(o.status));
 #pragma unroll
-    for (int q = 0; q < 6; ++q) sc[(1 + q) * P.n_pad] = o.norm[q];
-    sc[7 * P.n_pad] = o.sin_h;
-    sc[8 * P.n_pad] = o.cos_h;
+    for (int q = 0; q < 6; ++q) st_stream(sc + (1 + q) * P.n_pad, o.norm[q]);
+    st_stream(sc + 7 * P.n_pad, o.sin_h);
+    st_stream(sc + 8 * P.n_pad, o.cos_h);
 }
 
 template <int NV, bool MOD, int PAC>
@@ -552,6 +557,9 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
     if (P.has_penalty) P.nchg[e] = 0;
 }
 
+#ifndef PTG_ORDER
+#define PTG_ORDER 0      // 0: windows staged before the plant transition | 1: transition first, RNG record requested early
+#endif
 #ifndef PTG_STEP_MIN_BLOCKS
 #define PTG_STEP_MIN_BLOCKS 4        // CTAs of 256 threads per SM the step kernel is compiled for (<= 64 registers)
 #endif
@@ -608,8 +616,14 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         const int prev_state = meta & 7;
         const Plan plan = plan_transition(action, meta, tinfo & 7);
         int lut_val = 0;
-        if (plan.col >= 0) lut_val = __ldg(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + plan.col);
-        if (plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF) prefetch_l1(P.rng + e);
+        if (plan.col >= 0) lut_val = ldg32_nc_keep(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + plan.col);
+        const bool draws = plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF;
+        RngLoad rl = {};
+#if PTG_ORDER == 1
+        if (draws) rl = request_rng(P, e);            // both sectors of the RNG record, in flight with everything below
+#else
+        if (draws) prefetch_l1(P.rng + e);
+#endif
         // (2) clock of step k+1 (:442-445, integer form of floor(clock_hours), floor(clock_days)) -> market rows of
         //     the NEW hour/day (:446-447) -> observation windows; sin/cos of the clock come from the clock table
         const unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
@@ -618,15 +632,39 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         load_hour_row<NV>(P, t_hour, hrow);
         day = load_day_row(P, t_day);
         const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + (k + 1)));
+#if PTG_ORDER == 0
         stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
         const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
-        // (3) plant transition -> step-table entry (2 x 32 B = two sectors)
-        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi);
-        const int state_change = (prev_state != (int)(meta & 7));
-        const U256 qc = ldg256_nc(P.step_tab + ent);                                    // c_gas, c_eua, c_el, c_0
-        const U256 qn = ldg256_nc(reinterpret_cast<const char*>(P.step_tab + ent) + 32);  // norm[6], tinfo, pad
-        // (4) window tiles -> TMA while the gather above is in flight (the warp reconverges here)
         if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
+#endif
+        // (3) plant transition -> step-table entry (2 x 32 B = two sectors)
+        const int ent = apply_transition<PTG_ORDER == 1>(P, e, plan, i, j, meta, lut_val, zig_kiwi, rl);
+        const int state_change = (prev_state != (int)(meta & 7));
+        U256 qc, qn;      // qc = {c_gas, c_eua, c_el, c_0}, qn = {norm[6], tinfo, pad}
+        if (nvalid == 32) {
+            // L1TEX cost of a gather is per (instruction, 128 B line): a lane pair splits its two entries so that
+            // each LDG.256 touches 16 lines instead of 32 (even lane: first halves, odd lane: second halves), then
+            // the halves are exchanged with four 64-bit shuffles
+            const int ent_p = __shfl_xor_sync(0xffffffffu, ent, 1);
+            const bool odd = lane & 1;
+            const char* base = reinterpret_cast<const char*>(P.step_tab) + (odd ? 32 : 0);
+            const U256 a = ldg256_nc(base + (int64_t)(odd ? ent_p : ent) * 64);     // the even lane's entry
+            const U256 b = ldg256_nc(base + (int64_t)(odd ? ent : ent_p) * 64);     // the odd lane's entry
+            U256 snd = odd ? a : b, rcv;
+            rcv.a = __shfl_xor_sync(0xffffffffu, snd.a, 1); rcv.b = __shfl_xor_sync(0xffffffffu, snd.b, 1);
+            rcv.c = __shfl_xor_sync(0xffffffffu, snd.c, 1); rcv.d = __shfl_xor_sync(0xffffffffu, snd.d, 1);
+            qc = odd ? rcv : a;
+            qn = odd ? b : rcv;
+        } else {
+            qc = ldg256_nc(P.step_tab + ent);
+            qn = ldg256_nc(reinterpret_cast<const char*>(P.step_tab + ent) + 32);
+        }
+#if PTG_ORDER == 1
+        // the windows are staged and handed to the TMA while the step-table gather is in flight
+        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
+        const double el = hour_row_el<NV>(hrow);
+        if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
+#endif
         // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
         const double c_gas = __longlong_as_double((long long)qc.a), c_eua = __longlong_as_double((long long)qc.b);
         const double c_el = __longlong_as_double((long long)qc.c), c_0 = __longlong_as_double((long long)qc.d);
@@ -680,8 +718,8 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
     }
     if (active) {
         store_obs_scalars<MOD>(P, obs_out, e, day, o);
-        rew_out[e] = reward;
-        done_out[e] = (uint8_t)done;
+        st_stream(rew_out + e, reward);
+        st_stream(done_out + e, (uint8_t)done);
     }
 }
 
@@ -743,9 +781,9 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
         }
     }
     if (active) {
-        P.core[e] = make_int4(i, j, k, (int)meta);
-        P.tinfo[e] = tinfo;
-        P.ep_ret[e] = ep_ret;
+        st_stream(P.core + e, make_int4(i, j, k, (int)meta));
+        st_stream(P.tinfo + e, tinfo);
+        st_stream(P.ep_ret + e, ep_ret);
     }
     if (lane == 0) tma_store_wait_read();               // the staging buffer must outlive the bulk stores' reads
 }
