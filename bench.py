@@ -35,6 +35,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 1 << 20
+# Algorithmic HBM bytes of one transition-noise draw (numpy-exact PCG64 state lives in HBM per env): PCG64 state
+# 16 B read + 16 B written, increment 16 B read, draw counter 8 B read + 8 B written.
+RNG_BYTES_PER_DRAW = 64
 WORKLOAD = "BS2/OP2 mod, discrete int64 actions, train episodes, synthetic data of repo shapes"
 METRIC, UNIT = "env-steps/sec", "env-steps/s"
 
@@ -163,8 +166,25 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing (value, roofline) ----------------
+    def total_draws():
+        return int(env.get_state()["draws"].sum())
+
+    def timed(pool_, n_steps):
+        for t in range(W):
+            env.step_tensor(pool_[t % n_pool])
+        torch.cuda.synchronize()
+        d0 = total_draws()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for t in range(n_steps):
+            env.step_tensor(pool_[t % n_pool])
+        a1.record()
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1) / n_steps, (total_draws() - d0) / (n_steps * n_local)
+
     for t in range(W):
         env.step_tensor(pool[t % n_pool])
+    draws0 = total_draws()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -179,18 +199,16 @@ def run_gpu(args):
     launches = env.kernel_launches() - l0
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    # secondary: an agent-like "sticky" policy (each env repeats one action; no transition noise after warm-up)
+    draws_per_step = (total_draws() - draws0) / (K * n_local)
+    # secondary action distributions: the load-biased mix, and an agent-like "sticky" policy (each
+    # env repeats one action, so almost no transition noise is drawn after warm-up)
+    Ks = max(50, K // 4)
+    probs = torch.tensor([.05, .05, .3, .3, .3], device=dev)
+    biased = torch.multinomial(probs, n_pool * n_local, replacement=True, generator=g).view(n_pool, n_local)
+    biased_ms, biased_draws = timed(biased, Ks)
+    del biased
     sticky = pool[:1].repeat(n_pool, 1).contiguous()
-    for t in range(W):
-        env.step_tensor(sticky[t % n_pool])
-    torch.cuda.synchronize()
-    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    es0.record()
-    for t in range(K):
-        env.step_tensor(sticky[t % n_pool])
-    es1.record()
-    torch.cuda.synchronize()
-    sticky_ms = es0.elapsed_time(es1) / K
+    sticky_ms, sticky_draws = timed(sticky, Ks)
     del sticky
     env.poll_error()
     stats = env.episode_stats(clear=True)       # the path's only collective: one 64-byte all-gather per roll-out
@@ -237,13 +255,19 @@ def run_gpu(args):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        bpe = env.bytes_per_env_step
+        bpe0 = env.bytes_per_env_step                        # state + action + observation + reward/done
+        bpe = bpe0 + RNG_BYTES_PER_DRAW * draws_per_step     # + the RNG state of the env-steps that draw noise
         kernel_ms = ms / K                                   # rank 0's own kernel time (CUDA events, same stream)
         achieved = bpe * n_local / (kernel_ms * 1e-3) / 1e9
+
+        def frac_of(ms_, draws_):
+            return (bpe0 + RNG_BYTES_PER_DRAW * draws_) * n_local / (ms_ * 1e-3) / 1e9 / peak
+
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
-        if os.path.exists(tp):
-            with open(tp) as fh:
+        tps = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("traffic_r")) \
+            if os.path.isdir(os.path.join(ROOT, "profiles")) else []
+        if tps:
+            with open(os.path.join(ROOT, "profiles", tps[-1])) as fh:
                 traffic = json.load(fh).get("dram_bytes_per_launch")
         cores = len(os.sched_getaffinity(0))
         cpu = None
@@ -260,14 +284,22 @@ def run_gpu(args):
             "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": n_local, "envs_total": n_global,
-                       "obs_dim": env.obs_dim, "bytes_per_env_step": bpe, "noise": "on-device PCG64+ziggurat (numpy-exact)",
+                       "obs_dim": env.obs_dim, "noise": "on-device PCG64+ziggurat (numpy-exact)",
+                       "bytes_per_env_step": round(bpe, 2),
+                       "bytes_per_env_step_breakdown": {"state_action_obs_reward_done": bpe0,
+                                                        "rng_state_per_draw": RNG_BYTES_PER_DRAW,
+                                                        "draws_per_env_step": round(draws_per_step, 4)},
                        "l2": f"per-step traffic {bpe * n_local / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
                        "actions": "uniform random over the 5 actions (worst case: ~38% of env-steps redraw noise)",
-                       "sticky_policy_ms_per_step": sticky_ms,
-                       "sticky_policy_roofline_frac": bpe * n_local / (sticky_ms * 1e-3) / 1e9 / peak,
+                       "roofline_frac_excluding_rng_bytes": bpe0 * n_local / (kernel_ms * 1e-3) / 1e9 / peak,
+                       "load_biased_mix": {"p": [.05, .05, .3, .3, .3], "ms_per_step": biased_ms,
+                                           "draws_per_env_step": round(biased_draws, 4),
+                                           "roofline_frac": frac_of(biased_ms, biased_draws)},
+                       "sticky_policy": {"ms_per_step": sticky_ms, "draws_per_env_step": round(sticky_draws, 4),
+                                         "roofline_frac": frac_of(sticky_ms, sticky_draws)},
                        "rollout_kernel_ms_per_step": roll_ms, "episodes_finished": stats["episodes"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_step<4,true>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_step<4,true,false,false,13>",
                          "kernel_ms": kernel_ms},
             "cpu_baseline": cpu,
             "e2e": {"value": n_global * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,

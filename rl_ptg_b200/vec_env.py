@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import time
+from collections.abc import Sequence as _SequenceABC
 from typing import Any, Sequence
 
 import numpy as np
@@ -44,6 +45,35 @@ def shard_range(n_envs_global: int, rank: int, world_size: int) -> tuple[int, in
     base, rem = divmod(int(n_envs_global), int(world_size))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+class LazyInfos(_SequenceABC):
+    """``infos`` of a large batch: behaves like the list of per-env dicts SB3 expects (``len``, indexing, iteration)
+    but only materialises the dicts that are looked at.  Train mode: ``{}`` everywhere except the envs whose
+    episode just ended; eval mode: the 24-field dict of ``ptg_gym_env.py:253-278`` built on demand from the host
+    copy of the info array."""
+
+    __slots__ = ("_n", "_over", "_make")
+
+    def __init__(self, n: int, overrides: dict | None = None, make=None):
+        self._n, self._over, self._make = n, overrides or {}, make
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):
+            return [self[q] for q in range(*idx.indices(self._n))]
+        idx = int(idx)
+        if idx < 0:
+            idx += self._n
+        if not 0 <= idx < self._n:
+            raise IndexError(idx)
+        d = self._over.get(idx)
+        if d is None:
+            d = self._make(idx) if self._make is not None else {}
+            self._over[idx] = d          # identity is stable: callers may annotate the dict they were handed
+        return d
 
 
 class _VecEnvBase:
@@ -158,7 +188,7 @@ class PtGVecEnv(_Base):
         self._act_d = torch.zeros(n, dtype=act_dtype, device=dev)
         self._tape = None
         self._t_start = time.time()
-        self._empty_infos = [{} for _ in range(n)]
+        self._ev_small = torch.cuda.Event()
         self.bytes_per_env_step = int(self._L.ptg_bytes_per_env_step(self._h, _TORCH_ACT[act_dtype]))
         if seed is not None:
             self.seed(seed)
@@ -227,12 +257,14 @@ class PtGVecEnv(_Base):
         self.reset_tensor(_return_views=False)
         obs_h = self._next_obs_host()
         obs_h.copy_(self._obs, non_blocking=True)
-        want_info = self.num_envs <= self.info_limit
-        if want_info:
-            self._info_h.copy_(self._info, non_blocking=True)
+        self._info_h.copy_(self._info, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         self.poll_error()
-        self.reset_infos = self._info_dicts(range(self.num_envs)) if want_info else [{} for _ in range(self.num_envs)]
+        if self.num_envs <= self.info_limit:      # reset() returns the full info dict even in train mode (:503-506)
+            self.reset_infos = self._info_dicts(range(self.num_envs))
+        else:
+            snap = self._info_h.numpy().copy()
+            self.reset_infos = LazyInfos(self.num_envs, None, lambda e, a=snap: self._info_dict(a[:, e]))
         return self._obs_numpy(obs_h)
 
     def step_async(self, actions) -> None:
@@ -249,33 +281,52 @@ class PtGVecEnv(_Base):
 
     def step_wait(self):
         obs_h = self._next_obs_host()
-        obs_h.copy_(self._obs, non_blocking=True)
-        self._reward_h.copy_(self._reward, non_blocking=True)
+        stream = torch.cuda.current_stream(self.device)
+        # small results first: the host can look at `dones` while the observation block is still in flight
         self._done_h.copy_(self._done, non_blocking=True)
+        self._reward_h.copy_(self._reward, non_blocking=True)
+        self._ev_small.record(stream)
+        obs_h.copy_(self._obs, non_blocking=True)
         eval_mode = bool(self.cfg.train_or_eval)
         if eval_mode:
             self._info_h.copy_(self._info, non_blocking=True)
-        stream = torch.cuda.current_stream(self.device)
-        stream.synchronize()
-        self.poll_error()
-        dones = self._done_h.numpy().astype(bool)
-        infos = self._info_dicts(range(self.num_envs)) if eval_mode else list(self._empty_infos)
-        if dones.any():
+        self._ev_small.synchronize()
+        dones = self._done_h.numpy().view(np.bool_).copy()
+        rewards = self._reward_h.numpy().copy()
+        any_done = bool(dones.any())
+        if any_done:
             self._term_obs_h.copy_(self._term_obs, non_blocking=True)
             self._ep_ret_h.copy_(self._ep_ret, non_blocking=True)
             self._ep_len_h.copy_(self._ep_len, non_blocking=True)
-            stream.synchronize()
-            idx = np.nonzero(dones)[0]
-            term = self._obs_numpy(self._term_obs_h, rows=idx)
-            t_now = round(time.time() - self._t_start, 6)
+        stream.synchronize()
+        self.poll_error()
+        lazy = self.num_envs > self.info_limit
+        # snapshots of what the dicts are built from (the pinned mirrors are overwritten by the next step)
+        info_a = None
+        if eval_mode:
+            info_a = self._info_h.numpy().copy() if lazy else self._info_h.numpy()
+        term = ret = length = None
+        if any_done:
+            term = self._obs_numpy(self._term_obs_h)
             ret, length = self._ep_ret_h.numpy(), self._ep_len_h.numpy()
-            for q, e in enumerate(idx):
-                d = dict(infos[e])
+            if lazy:
+                term = {k: v.copy() for k, v in term.items()}
+                ret, length = ret.copy(), length.copy()
+        t_now = round(time.time() - self._t_start, 6)
+
+        def make(e):
+            d = self._info_dict(info_a[:, e]) if info_a is not None else {}
+            if any_done and dones[e]:
                 d["episode"] = {"r": round(float(ret[e]), 6), "l": int(length[e]), "t": t_now}   # Monitor
                 d["TimeLimit.truncated"] = False                     # the env only ever terminates (:478-481)
-                d["terminal_observation"] = {k: v[q] for k, v in term.items()}
-                infos[e] = d
-        return self._obs_numpy(obs_h), self._reward_h.numpy().copy(), dones, infos
+                d["terminal_observation"] = {k: v[e] for k, v in term.items()}
+            return d
+
+        if lazy:
+            infos = LazyInfos(self.num_envs, None, make if (eval_mode or any_done) else None)
+        else:
+            infos = [make(e) for e in range(self.num_envs)]
+        return self._obs_numpy(obs_h), rewards, dones, infos
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None:
@@ -288,22 +339,22 @@ class PtGVecEnv(_Base):
         except Exception:
             pass
 
+    @staticmethod
+    def _info_dict(col) -> dict:
+        """One env's 24-field dict in the reference's key order (ptg_gym_env.py:253-278)."""
+        d = {}
+        for f, key in enumerate(_abi.INFO_KEYS):
+            if key in ("step", "Meth_State", "Meth_Hot_Cold"):
+                d[key] = int(col[f])
+            elif key == "Meth_Action":
+                d[key] = _abi.STATE_NAMES[int(col[f])]
+            else:
+                d[key] = float(col[f])
+        return d
+
     def _info_dicts(self, indices):
-        """24-field dicts in the reference's key order (ptg_gym_env.py:253-278) from the host info mirror."""
         arr = self._info_h.numpy()
-        out = []
-        for e in indices:
-            col = arr[:, e]
-            d = {}
-            for f, key in enumerate(_abi.INFO_KEYS):
-                if key in ("step", "Meth_State", "Meth_Hot_Cold"):
-                    d[key] = int(col[f])
-                elif key == "Meth_Action":
-                    d[key] = _abi.STATE_NAMES[int(col[f])]
-                else:
-                    d[key] = float(col[f])
-            out.append(d)
-        return out
+        return [self._info_dict(arr[:, e]) for e in indices]
 
     _STATE_ATTRS = {"Meth_State": "meth_state", "i": "i", "j": "j", "k": "k", "hot_cold": "hot_cold",
                     "Meth_T_cat": "t_cat", "act_ep_h": "act_ep_h", "act_ep_d": "act_ep_d", "cum_rew": "cum_reward"}
