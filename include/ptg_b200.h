@@ -209,6 +209,37 @@ int ptg_episode_stats(PtgHandle* h, PtgEpisodeStats* stats_dev, int clear, void*
 /* Host-side combine of per-rank stats (sum / min / max), e.g. after an NCCL all-gather of the 64-byte structs. */
 void ptg_stats_combine(const PtgEpisodeStats* per_rank, int n_ranks, PtgEpisodeStats* out);
 
+/* ---- callers either side of the path; all pointers are device memory unless noted ----------- */
+
+/* SB3 VecNormalize(venv, norm_obs=False) as the reference wraps every env (src/rl_utils.py:453, :491; defaults
+ * norm_reward=True, clip_reward=10, gamma=0.99, epsilon=1e-8), split so that the batch moments can be exchanged
+ * between ranks (one 24-byte all-gather) before they are folded into the running statistics:
+ *   ptg_vecnorm_moments : returns = returns * gamma + reward (VecNormalize._update_reward); moments_out[3] =
+ *                         {count, mean, sum of squared deviations} of the new returns (deterministic tree)
+ *   ptg_vecnorm_apply   : RunningMeanStd.update_from_moments with `n_batch` such records (training != 0), then
+ *                         reward_out = clip(reward_in / sqrt(var + epsilon), +-clip_reward); returns[done] = 0.
+ *                         st_in / st_out: {mean, var, count, pad} fp64, distinct buffers (ping-pong). */
+int ptg_vecnorm_moments(PtgHandle* h, const float* reward, double* returns, double gamma, double* moments_out,
+                        void* stream);
+int ptg_vecnorm_apply(PtgHandle* h, const float* reward_in, const uint8_t* done, double* returns, const double* st_in,
+                      double* st_out, const double* moments, int32_t n_batch, int32_t training, double epsilon,
+                      double clip_reward, float* reward_out, void* stream);
+
+/* The flat feature rows SB3's MultiInputPolicy (CombinedExtractor) builds from the Dict observation: keys in the
+ * sorted order of the gymnasium Dict space, METH_STATUS one-hot(6).  feat: [n_envs][ptg_features_dim()] fp32.
+ *   mod: CH4_syn, Elec_Heating, H2O_DE, H2_in, H2_res, METH_STATUS[6], Part_Full[pa], Pot_Reward[pa], T_CAT, cos, sin
+ *   raw: CH4_syn, EUA_Price[2], Elec_Heating, Elec_Price[pa], Gas_Price[2], H2O_DE, H2_in, H2_res, METH_STATUS[6],
+ *        T_CAT, cos, sin */
+int ptg_features_dim(const PtgHandle* h);
+int ptg_features(PtgHandle* h, const float* obs, float* feat, void* stream);
+
+/* SB3 RolloutBuffer.compute_returns_and_advantage (GAE(lambda)) over [T][n_envs] roll-out buffers, in numpy's
+ * evaluation order and dtypes (float32 buffers, float64 carry).  PPO hyper-parameters of the reference:
+ * config/config_agent.yaml:46,53 (gamma 0.973, gae_lambda 0.8002). */
+int ptg_gae(int64_t n_envs, int32_t T, const float* rewards, const float* values, const uint8_t* episode_starts,
+            const float* last_values, const uint8_t* last_dones, double gamma, double gae_lambda, float* advantages,
+            float* returns, void* stream);
+
 /* Sticky device-side error word (invalid action, market-table overrun, tape overrun).  Synchronises `stream`.
  * Returns PTG_OK or the first error seen since the last poll and clears it. */
 int ptg_poll_error(PtgHandle* h, void* stream);

@@ -16,7 +16,7 @@ EXPORTS = (
     "ptg_set_state", "ptg_episode_stats", "ptg_stats_combine", "ptg_poll_error", "ptg_obs_dim", "ptg_obs_layout",
     "ptg_obs_elems", "ptg_num_envs", "ptg_bytes_per_env_step", "ptg_kernel_launches", "ptg_host_standard_normal",
     "ptg_host_seed_state", "ptg_last_error",
-    "ptg_abi_version",
+    "ptg_abi_version", "ptg_vecnorm_moments", "ptg_vecnorm_apply", "ptg_features_dim", "ptg_features", "ptg_gae",
 )
 
 
@@ -56,6 +56,12 @@ def load(build_if_missing: bool = False):
     L.ptg_stats_combine.argtypes = [C.POINTER(_abi.PtgEpisodeStats), i32, C.POINTER(_abi.PtgEpisodeStats)]
     L.ptg_stats_combine.restype = None
     L.ptg_poll_error.argtypes = [vp, vp]
+    f64 = C.c_double
+    L.ptg_vecnorm_moments.argtypes = [vp, vp, vp, f64, vp, vp]
+    L.ptg_vecnorm_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, f64, f64, vp, vp]
+    L.ptg_features_dim.argtypes = [vp]
+    L.ptg_features.argtypes = [vp, vp, vp, vp]
+    L.ptg_gae.argtypes = [i64, C.c_int32, vp, vp, vp, vp, vp, f64, f64, vp, vp, vp]
     L.ptg_obs_dim.argtypes = [vp]
     L.ptg_obs_layout.argtypes = [vp, C.POINTER(_abi.PtgObsKey), i32]
     L.ptg_obs_elems.argtypes = [vp]

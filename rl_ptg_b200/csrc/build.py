@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libptg_b200.so")
 SOURCES = ["ptg_capi.cu"]
-DEPS = ["ptg_capi.cu", "ptg_kernels.cuh", "ptg_device.cuh", "ptg_rng.cuh", "ptg_ziggurat_tables.h",
+DEPS = ["ptg_capi.cu", "ptg_kernels.cuh", "ptg_train.cuh", "ptg_device.cuh", "ptg_rng.cuh", "ptg_ziggurat_tables.h",
         os.path.join("..", "..", "include", "ptg_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "ptg_kernels.cuh"
+#include "ptg_train.cuh"
 #include "ptg_ziggurat_tables.h"
 
 namespace {
@@ -40,6 +41,7 @@ struct PtgHandle {
     int64_t* d_seeds = nullptr;
     uint8_t* d_mask = nullptr;
     StatAcc* d_partial = nullptr;
+    Moments* d_vn_partial = nullptr;  // per-CTA moments of the VecNormalize returns
     uint32_t* d_err = nullptr;
     int32_t* d_state_i32 = nullptr;   // scratch for get/set state: 13 int32 arrays
     int64_t* d_state_i64 = nullptr;
@@ -364,6 +366,7 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     PTG_TRY(h->alloc(&P.fin_len_sum, n)); PTG_TRY(h->alloc(&P.fin_min, n)); PTG_TRY(h->alloc(&P.fin_max, n));
     PTG_TRY(h->alloc(&h->d_seeds, n)); PTG_TRY(h->alloc(&h->d_mask, n));
     PTG_TRY(h->alloc(&h->d_partial, PTG_STATS_BLOCKS));
+    PTG_TRY(h->alloc(&h->d_vn_partial, PTG_STATS_BLOCKS));
     PTG_TRY(h->alloc(&h->d_state_i32, n * 13)); PTG_TRY(h->alloc(&h->d_state_i64, n)); PTG_TRY(h->alloc(&h->d_state_f64, n * 2));
     P.tape = nullptr; P.tape_len = 0;
     {   // one scheduling wave = resident CTAs of the step kernel on this device
@@ -528,6 +531,63 @@ extern "C" int ptg_episode_stats(PtgHandle* h, PtgEpisodeStats* stats_dev, int c
     k_stats_final<<<1, 256, 0, st>>>(h->d_partial, PTG_STATS_BLOCKS, h->total_steps, stats_dev);
     h->launches += 2;
     if (clear) h->total_steps = 0.0;
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// callers either side of the path: VecNormalize (reward), flat policy features, GAE
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int ptg_vecnorm_moments(PtgHandle* h, const float* reward, double* returns, double gamma,
+                                   double* moments_out, void* stream) {
+    if (!h || !reward || !returns || !moments_out) return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    k_vecnorm_returns<<<PTG_STATS_BLOCKS, 256, 0, st>>>(h->P.n_envs, reward, returns, gamma, h->d_vn_partial);
+    k_vecnorm_moments<<<1, 256, 0, st>>>(h->d_vn_partial, PTG_STATS_BLOCKS, reinterpret_cast<Moments*>(moments_out));
+    h->launches += 2;
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
+extern "C" int ptg_vecnorm_apply(PtgHandle* h, const float* reward_in, const uint8_t* done, double* returns,
+                                 const double* st_in, double* st_out, const double* moments, int32_t n_batch,
+                                 int32_t training, double epsilon, double clip_reward, float* reward_out, void* stream) {
+    if (!h || !reward_in || !done || !returns || !st_in || !st_out || !reward_out)
+        return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
+    if (st_in == st_out) return fail(PTG_ERR_INVALID_ARGUMENT, "st_in and st_out must be distinct buffers");
+    if (training && (!moments || n_batch < 1)) return fail(PTG_ERR_INVALID_ARGUMENT, "training needs batch moments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    k_vecnorm_apply<<<blocks_for(h->P.n_envs, 256), 256, 0, st>>>(h->P.n_envs, reward_in, done, returns, st_in, st_out,
+                                                                 reinterpret_cast<const Moments*>(moments), n_batch,
+                                                                 training, epsilon, clip_reward, reward_out);
+    h->launches += 1;
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
+extern "C" int ptg_features_dim(const PtgHandle* h) {
+    if (!h) return 0;
+    return h->P.raw ? 18 + h->P.pa : 14 + 2 * h->P.pa;
+}
+
+extern "C" int ptg_features(PtgHandle* h, const float* obs, float* feat, void* stream) {
+    if (!h || !obs || !feat) return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
+    const int F = ptg_features_dim(h);
+    k_features<<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, (size_t)(PTG_BLOCK * F) * sizeof(float),
+                 static_cast<cudaStream_t>(stream)>>>(h->P, obs, feat, F);
+    h->launches += 1;
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
+extern "C" int ptg_gae(int64_t n_envs, int32_t T, const float* rewards, const float* values,
+                       const uint8_t* episode_starts, const float* last_values, const uint8_t* last_dones, double gamma,
+                       double gae_lambda, float* advantages, float* returns, void* stream) {
+    if (n_envs < 1 || T < 1) return fail(PTG_ERR_INVALID_ARGUMENT, "n_envs and T must be >= 1");
+    if (!rewards || !values || !episode_starts || !last_values || !last_dones || !advantages || !returns)
+        return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
+    k_gae<<<blocks_for(n_envs, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n_envs, T, rewards, values, episode_starts, last_values, last_dones, gamma, gae_lambda, advantages, returns);
     PTG_CUDA(cudaGetLastError());
     return PTG_OK;
 }

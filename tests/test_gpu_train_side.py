@@ -1,0 +1,113 @@
+"""-m gpu tests of the callers either side of the env path: VecNormalize reward
+normalisation, flat MultiInputPolicy features and GAE on the device, against the numpy restatement of the
+Stable-Baselines3 algorithms in oracle/sb3_restated.py (parity unpinned: SB3 itself is not installed here).
+
+Tolerances: VecNormalize statistics 1e-10 relative (fp64, different but deterministic summation tree);
+normalised rewards 1e-6 relative (fp32 output); features bit-exact; GAE 1e-6 relative (fp32 buffers)."""
+import numpy as np
+import pytest
+
+from helpers import synthetic_kwargs
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(n, overrides=None, **kw):
+    from rl_ptg_b200.vec_env import PtGVecEnv
+    return PtGVecEnv(synthetic_kwargs(overrides or dict(scenario=2, operation="OP2")), n, seed=3654, **kw)
+
+
+@pytest.mark.parametrize("n_envs", [6, 1000, 70001])
+def test_vecnormalize_reward_matches_sb3_restatement(n_envs):
+    import torch
+    from oracle.sb3_restated import VecNormalizeRewardRef
+    from rl_ptg_b200.vec_normalize import VecNormalizeReward
+    env = _env(n_envs)
+    vn = VecNormalizeReward(env, gamma=0.99, clip_reward=10.0)
+    ref = VecNormalizeRewardRef(n_envs, gamma=0.99, clip_reward=10.0)
+    vn.reset_tensor()
+    g = torch.Generator(device=env.device); g.manual_seed(7)
+    for t in range(40):
+        a = torch.randint(0, 5, (n_envs,), generator=g, device=env.device)
+        _, nrew, done = vn.step_tensor(a)
+        raw = env._reward.cpu().numpy()
+        want = ref.step(raw.astype(np.float32), done.cpu().numpy().astype(bool))
+        got = nrew.cpu().numpy()
+        assert np.allclose(got, want, rtol=1e-6, atol=1e-9), f"step {t}"
+        assert np.isclose(vn.ret_rms.mean, ref.ret_rms.mean, rtol=1e-10, atol=1e-13)
+        assert np.isclose(vn.ret_rms.var, ref.ret_rms.var, rtol=1e-10)
+        assert np.isclose(vn.ret_rms.count, ref.ret_rms.count, rtol=1e-14)
+        assert np.allclose(vn.returns.cpu().numpy(), ref.returns, rtol=1e-12, atol=1e-12)
+    # evaluation mode: statistics frozen, normalisation still applied (SB3: env.training = False)
+    vn.training = ref.training = False
+    before = (vn.ret_rms.mean, vn.ret_rms.var, vn.ret_rms.count)
+    a = torch.randint(0, 5, (n_envs,), generator=g, device=env.device)
+    _, nrew, done = vn.step_tensor(a)
+    want = ref.step(env._reward.cpu().numpy(), done.cpu().numpy().astype(bool))
+    assert np.allclose(nrew.cpu().numpy(), want, rtol=1e-6, atol=1e-9)
+    assert before == (vn.ret_rms.mean, vn.ret_rms.var, vn.ret_rms.count)
+    env.close()
+
+
+def test_vecnormalize_is_bit_reproducible():
+    import torch
+    from rl_ptg_b200.vec_normalize import VecNormalizeReward
+    outs = []
+    for _ in range(2):
+        env = _env(50000)
+        vn = VecNormalizeReward(env)
+        vn.reset_tensor()
+        g = torch.Generator(device=env.device); g.manual_seed(3)
+        for t in range(10):
+            _, r, _ = vn.step_tensor(torch.randint(0, 5, (50000,), generator=g, device=env.device))
+        outs.append((r.cpu().numpy().copy(), vn.ret_rms.mean, vn.ret_rms.var))
+        env.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1:] == outs[1][1:]
+
+
+@pytest.mark.parametrize("overrides", [dict(scenario=2, operation="OP2"),
+                                       dict(scenario=1, operation="OP1", raw_modified="raw"),
+                                       dict(scenario=3, operation="OP2", price_ahead=6),
+                                       dict(scenario=1, operation="OP2", raw_modified="raw", price_ahead=16)])
+@pytest.mark.parametrize("n_envs", [5, 257, 4099])
+def test_flat_features_match_combined_extractor(overrides, n_envs):
+    import torch
+    from oracle.sb3_restated import combined_extractor_ref
+    from rl_ptg_b200.vec_normalize import feature_dim, feature_names, features_tensor
+    env = _env(n_envs, overrides)
+    obs = env.reset()
+    F = feature_dim(env)
+    assert len(feature_names(env)) == F
+    g = torch.Generator(device=env.device); g.manual_seed(1)
+    for t in range(6):
+        want = combined_extractor_ref(obs)
+        got = features_tensor(env).cpu().numpy()
+        assert got.shape == (n_envs, F) == want.shape
+        assert np.array_equal(got, want), f"features differ at step {t}"
+        a = torch.randint(0, 5, (n_envs,), generator=g, device=env.device).cpu().numpy()
+        obs, _, _, _ = env.step(a)
+    env.close()
+
+
+@pytest.mark.parametrize("T,n", [(1, 7), (5, 1000), (64, 5003)])
+def test_gae_matches_sb3_restatement(T, n):
+    import torch
+    from oracle.sb3_restated import gae_ref
+    from rl_ptg_b200.vec_normalize import gae
+    rng = np.random.default_rng(T * 1000 + n)
+    rewards = rng.normal(0, 1, (T, n)).astype(np.float32)
+    values = rng.normal(0, 2, (T, n)).astype(np.float32)
+    starts = (rng.random((T, n)) < 0.05).astype(np.float32)
+    last_values = rng.normal(0, 2, n).astype(np.float32)
+    dones = rng.random(n) < 0.1
+    gamma, lam = 0.973, 0.8002            # config/config_agent.yaml:46,53
+    want_adv, want_ret = gae_ref(rewards, values, starts, last_values, dones, gamma, lam)
+    dev = "cuda:0"
+    adv, ret = gae(torch.from_numpy(rewards).to(dev), torch.from_numpy(values).to(dev),
+                   torch.from_numpy(starts.astype(np.uint8)).to(dev), torch.from_numpy(last_values).to(dev),
+                   torch.from_numpy(dones.astype(np.uint8)).to(dev), gamma, lam)
+    assert np.allclose(adv.cpu().numpy(), want_adv, rtol=1e-6, atol=1e-6)
+    assert np.allclose(ret.cpu().numpy(), want_ret, rtol=1e-6, atol=1e-6)
+    # evaluation order and dtypes follow numpy's: expect (near) bit equality, report the fraction that is exact
+    exact = np.mean(adv.cpu().numpy() == want_adv)
+    assert exact > 0.999, f"only {exact:.4f} of the advantages are bit-identical"
