@@ -313,6 +313,132 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json config 5: end-to-end PPO training, GPU VecEnv feeding the torch policy vs the CPU env baseline
+# ---------------------------------------------------------------------------------------------------------------
+PPO_METRIC = "PPO training env-steps/sec"
+
+
+def run_ppo_gpu(args):
+    """PPO (SB3 algorithm, reference hyper-parameters except the roll-out geometry) with env, VecNormalize, feature
+    rows and GAE on the device.  One "step" = one PPO iteration (collect n_steps x n_envs, then n_epochs of updates)."""
+    import torch
+    from rl_ptg_b200.ppo import PPO, reference_hyper_kwargs
+    from rl_ptg_b200.vec_env import PtGVecEnv
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    kw = make_kwargs()
+    hyper = reference_hyper_kwargs()
+    hyper.update(n_steps=args.ppo_n_steps, batch_size=args.ppo_batch, n_epochs=args.ppo_epochs, seed=3654)
+    env = PtGVecEnv(kw, args.ppo_envs, seed=3654, device=dev)
+    model = PPO(env, **hyper)
+    per_iter = args.ppo_envs * args.ppo_n_steps
+    model.learn(per_iter * max(1, args.warmup if args.warmup < 3 else 1))      # warm-up iteration(s): cuBLAS, allocator
+    torch.cuda.synchronize()
+    t0, n0 = time.perf_counter(), model.num_timesteps
+    tc = 0.0
+    iters = max(1, min(args.steps, args.ppo_iters))
+    for _ in range(iters):
+        c0 = time.perf_counter()
+        model.collect_rollouts()
+        torch.cuda.synchronize()
+        tc += time.perf_counter() - c0
+        model.train()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    steps_done = model.num_timesteps - n0
+    ep = env.episode_stats(clear=True, reduce=False)
+    _emit({"metric": PPO_METRIC, "value": steps_done / dt, "unit": UNIT, "n_gpus": 1, "steps": iters,
+           "warmup": 1, "ms_per_step": 1e3 * dt / iters, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": steps_done / dt / 166.6, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "PPO (MultiInputPolicy 2x358 ReLU) on BS2/OP2 mod, GPU VecEnv + VecNormalize + "
+                                  "feature rows + GAE on device", "n_envs": args.ppo_envs, "n_steps": args.ppo_n_steps,
+                      "batch_size": args.ppo_batch, "n_epochs": args.ppo_epochs,
+                      "collect_env_steps_per_s": steps_done / tc, "collect_share_of_time": tc / dt,
+                      "baseline_note": "vs_baseline = value / 166.6 env-steps/s, the reference's shipped TensorBoard "
+                                       "time/fps (BASELINE.md; unknown hardware, 6 envs)",
+                      "episodes_finished": ep["episodes"], "ep_rew_mean": ep["return_mean"]},
+           "gpu_launches": env.kernel_launches()})
+    env.close()
+
+
+def run_ppo_reference(args):
+    """The reference's arrangement: the env on the host cores (CPU oracle, one thread per env like SubprocVecEnv
+    workers, without the pickling), observations to the torch policy and actions back every step, VecNormalize and
+    GAE in numpy (SB3's own code path, restated), the same PPO update.  Reference hyper-parameters
+    (config_agent.yaml: 6 envs, n_steps 4263, batch 203, 13 epochs) unless overridden."""
+    import torch
+    from oracle.ptg_oracle import OracleVecEnv, draw_noise_tape
+    from oracle.sb3_restated import VecNormalizeRewardRef, gae_ref
+    from rl_ptg_b200.ppo import PPOCore, reference_hyper_kwargs
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    kw = make_kwargs()
+    n, T = args.ppo_ref_envs, args.ppo_ref_n_steps
+    hyper = reference_hyper_kwargs()
+    hyper.update(n_steps=T, seed=3654)
+    pa = int(kw["price_ahead"])
+    F = 14 + 2 * pa
+    # oracle obs columns (reference key order) -> sorted-key feature columns
+    o_pot, o_pf, o_st = np.arange(0, pa), np.arange(pa, 2 * pa), 2 * pa
+    o_T, o_h2, o_ch4, o_h2res, o_h2o, o_heat, o_sin, o_cos = (2 * pa + 1 + q for q in range(8))
+    iters = max(1, min(args.steps, args.ppo_iters))
+    tape = draw_noise_tape(3654 + np.arange(n), kw["noise"], T * (iters + 1) + 8)
+    cores = len(os.sched_getaffinity(0))
+    env = OracleVecEnv(kw, n, noise_tape=tape, threads=min(cores, n))
+    model = PPOCore(n, F, dev, **hyper)
+    vn = VecNormalizeRewardRef(n)
+
+    def features(obs):
+        f = np.zeros((n, F), np.float32)
+        f[:, 0], f[:, 1], f[:, 2], f[:, 3], f[:, 4] = obs[:, o_ch4], obs[:, o_heat], obs[:, o_h2o], obs[:, o_h2], obs[:, o_h2res]
+        f[np.arange(n), 5 + obs[:, o_st].astype(np.int64)] = 1.0
+        f[:, 11:11 + pa], f[:, 11 + pa:11 + 2 * pa] = obs[:, o_pf], obs[:, o_pot]
+        f[:, 11 + 2 * pa], f[:, 12 + 2 * pa], f[:, 13 + 2 * pa] = obs[:, o_T], obs[:, o_cos], obs[:, o_sin]
+        return f
+
+    obs = env.reset().copy()
+    starts = np.ones(n, np.float32)
+    rew_buf, val_buf, st_buf = np.zeros((T, n), np.float32), np.zeros((T, n), np.float32), np.zeros((T, n), np.float32)
+    t_all = t_col = 0.0
+    for it in range(iters + 1):                     # iteration 0 is the warm-up
+        c0 = time.perf_counter()
+        with torch.no_grad():
+            for t in range(T):
+                feat = torch.from_numpy(features(obs)).to(dev)
+                actions, values, logp = model.policy(feat)
+                model.buf_feat[t].copy_(feat); model.buf_actions[t].copy_(actions); model.buf_logp[t].copy_(logp)
+                val_buf[t] = values.cpu().numpy(); st_buf[t] = starts
+                o, r, d = env.step(actions.cpu().numpy())
+                rew_buf[t] = vn.step(r.astype(np.float32), d.astype(bool))
+                starts = d.astype(np.float32)
+                obs = o.copy()
+            last_values = model.policy.value(torch.from_numpy(features(obs)).to(dev)).cpu().numpy()
+        adv, ret = gae_ref(rew_buf, val_buf, st_buf, last_values, starts.astype(bool), model.gamma, model.gae_lambda)
+        model.buf_values.copy_(torch.from_numpy(val_buf)); model.buf_adv.copy_(torch.from_numpy(adv))
+        model.buf_ret.copy_(torch.from_numpy(ret))
+        c1 = time.perf_counter()
+        model.train()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        if it > 0:
+            t_col += c1 - c0
+            t_all += time.perf_counter() - c0
+    rate = iters * T * n / t_all
+    _emit({"impl": "reference", "metric": PPO_METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": iters,
+           "warmup": 1, "ms_per_step": 1e3 * t_all / iters, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": rate / 166.6, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "PPO (MultiInputPolicy 2x358 ReLU) on BS2/OP2 mod, env on host cores (CPU oracle), "
+                                  "policy on " + dev.type, "n_envs": n, "n_steps": T, "batch_size": hyper["batch_size"],
+                      "n_epochs": hyper["n_epochs"], "collect_env_steps_per_s": iters * T * n / t_col,
+                      "collect_share_of_time": t_col / t_all},
+           "cpu_baseline": {"value": rate, "unit": UNIT, "cores": min(cores, n), "kind": "port",
+                            "sample": f"{iters} PPO iteration(s) of {T} x {n} env-steps"},
+           "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+    env.close()
+
+
 _REAL_STDOUT = None
 
 
@@ -345,9 +471,20 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rollout", action="store_true", default=True)
     ap.add_argument("--no-rollout", dest="rollout", action="store_false")
+    ap.add_argument("--workload", default="env", choices=["env", "ppo"],
+                    help="env: the north-star env-steps/s bench (default) | ppo: BASELINE.json config 5")
+    ap.add_argument("--ppo-envs", type=int, default=65536)
+    ap.add_argument("--ppo-n-steps", type=int, default=32)
+    ap.add_argument("--ppo-batch", type=int, default=65536)
+    ap.add_argument("--ppo-epochs", type=int, default=13)
+    ap.add_argument("--ppo-iters", type=int, default=4)
+    ap.add_argument("--ppo-ref-envs", type=int, default=6)
+    ap.add_argument("--ppo-ref-n-steps", type=int, default=4263)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "ppo":
+        run_ppo_reference(args) if args.impl == "reference" else run_ppo_gpu(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

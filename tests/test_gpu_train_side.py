@@ -111,3 +111,35 @@ def test_gae_matches_sb3_restatement(T, n):
     # evaluation order and dtypes follow numpy's: expect (near) bit equality, report the fraction that is exact
     exact = np.mean(adv.cpu().numpy() == want_adv)
     assert exact > 0.999, f"only {exact:.4f} of the advantages are bit-identical"
+
+
+def test_ppo_rollout_buffers_are_consistent():
+    """Two PPO iterations on the device: the roll-out buffers obey the SB3 definitions (episode_starts shifted dones,
+    advantages = GAE of the stored rewards / values, stored rewards = VecNormalize of the env rewards) and the update
+    moves the policy."""
+    import torch
+    from oracle.sb3_restated import gae_ref
+    from rl_ptg_b200.ppo import PPO, reference_hyper_kwargs
+    env = _env(512)
+    hyper = reference_hyper_kwargs()
+    hyper.update(n_steps=16, batch_size=1024, n_epochs=2, seed=1)
+    model = PPO(env, **hyper)
+    before = [p.detach().clone() for p in model.policy.parameters()]
+    model.collect_rollouts()
+    last_values = model.policy.value(model._last_feat).detach().cpu().numpy()
+    adv, ret = gae_ref(model.buf_rewards.cpu().numpy(), model.buf_values.cpu().numpy(),
+                       model.buf_starts.cpu().numpy().astype(np.float32), last_values,
+                       model._last_starts.cpu().numpy().astype(bool), model.gamma, model.gae_lambda)
+    assert np.allclose(model.buf_adv.cpu().numpy(), adv, rtol=1e-6, atol=1e-6)
+    assert np.allclose(model.buf_ret.cpu().numpy(), ret, rtol=1e-6, atol=1e-6)
+    assert model.buf_starts[0].all() and not model.buf_starts[1:].any()      # no episode ends within 16 steps
+    assert torch.isfinite(model.buf_feat).all() and model.buf_feat.shape == (16, 512, 40)
+    onehot = model.buf_feat[..., 5:11]
+    assert torch.equal(onehot.sum(-1), torch.ones_like(onehot[..., 0]))
+    assert (model.buf_rewards.abs() <= 10.0).all()                            # VecNormalize clip_reward
+    stats = model.train()
+    assert all(np.isfinite(v) for v in stats.values())
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.policy.parameters()))
+    model.learn(model.num_timesteps + 16 * 512)
+    assert model.logs and np.isfinite(model.logs[-1]["fps"])
+    env.close()
