@@ -1,6 +1,7 @@
 // ptg_capi.cu -- host side of libptg_b200.so: the C ABI declared in include/ptg_b200.h.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -372,7 +373,9 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     {   // one scheduling wave = resident CTAs of the step kernel on this device
         cudaDeviceProp prop{};
         PTG_TRY(cudaGetDeviceProperties(&prop, device));
-        P.prefetch_distance = prop.multiProcessorCount * PTG_STEP_MIN_BLOCKS * PTG_BLOCK;
+        double waves = 1.0;                       // PTG_PREFETCH_WAVES: kernel experiments only
+        if (const char* w = getenv("PTG_PREFETCH_WAVES")) waves = atof(w);
+        P.prefetch_distance = (int32_t)(waves * prop.multiProcessorCount * PTG_STEP_MIN_BLOCKS) * PTG_BLOCK;
     }
     k_construct<<<blocks_for(n_envs, 256), 256>>>(P);
     h->launches += 1;

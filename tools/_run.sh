@@ -1,4 +1,6 @@
-python -m pytest tests/test_gpu_train_side.py -m gpu -x -q -k ppo 2>&1 | tail -5
-python bench.py --workload ppo --steps 4 > gpurun_out/bench_ppo_gpu.json 2> gpurun_out/bench_ppo_err.log; cat gpurun_out/bench_ppo_gpu.json; tail -3 gpurun_out/bench_ppo_err.log
-python bench.py --workload ppo --ppo-envs 6 --ppo-n-steps 4263 --ppo-batch 203 --steps 1 > gpurun_out/bench_ppo_gpu_refhyper.json 2>> gpurun_out/bench_ppo_err.log; cat gpurun_out/bench_ppo_gpu_refhyper.json
-python bench.py --workload ppo --impl reference --steps 1 > gpurun_out/bench_ppo_ref.json 2>> gpurun_out/bench_ppo_err.log; cat gpurun_out/bench_ppo_ref.json; tail -3 gpurun_out/bench_ppo_err.log
+set -x
+CMD="python bench.py --steps 30 --warmup 3 --no-cpu-baseline --e2e-steps 3 --no-rollout"
+$CMD > gpurun_out/plain_r01b.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_r01b.csv $CMD > gpurun_out/ncu1_r01b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_step --launch-skip 10 --launch-count 2 -f -o gpurun_out/prof_step_r01b $CMD > gpurun_out/ncu2_r01b.log 2>&1
+tail -2 gpurun_out/ncu2_r01b.log
