@@ -72,19 +72,41 @@ struct PtgHandle {
 // ------------------------------------------------------------------------------------------------------------
 namespace {
 
+// Step kernels are launched with programmatic stream serialization (PDL): back-to-back steps overlap the next
+// launch's prologue with the current launch's tail wave (the kernel does griddepcontrol.wait before it reads state).
+template <typename K>
+void launch_pdl(K kernel, unsigned grid, cudaStream_t st, const DevParams& P, const void* actions, int adtype,
+                const PtgIO& io, int T) {
+#if PTG_PDL
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(PTG_BLOCK);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, P, actions, adtype, io, T);
+#else
+    kernel<<<grid, PTG_BLOCK, 0, st>>>(P, actions, adtype, io, T);
+#endif
+}
+
 template <int NV, bool MOD>
 void launch_step_t(PtgHandle* h, const void* actions, int adtype, const PtgIO& io, int T, cudaStream_t st) {
     const unsigned grid = blocks_for(h->P.n_envs, PTG_BLOCK);
     h->P.action_bytes = adtype == PTG_ACT_I64 ? 8 : adtype == PTG_ACT_U8 ? 1 : 4;
     const bool pa13 = NV == 4 && h->P.pa == 13;       // compile-time price_ahead for the reference default
     if (T > 0) {
-        if (pa13) k_step<NV, MOD, true, false, (NV == 4 ? 13 : 0)><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, T);
-        else k_step<NV, MOD, true, false, 0><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, T);
+        if (pa13) launch_pdl(k_step<NV, MOD, true, false, (NV == 4 ? 13 : 0)>, grid, st, h->P, actions, adtype, io, T);
+        else launch_pdl(k_step<NV, MOD, true, false, 0>, grid, st, h->P, actions, adtype, io, T);
     } else if (h->P.eval_mode && io.info) {
-        k_step<NV, MOD, false, true, 0><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, 1);
+        launch_pdl(k_step<NV, MOD, false, true, 0>, grid, st, h->P, actions, adtype, io, 1);
     } else {
-        if (pa13) k_step<NV, MOD, false, false, (NV == 4 ? 13 : 0)><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, 1);
-        else k_step<NV, MOD, false, false, 0><<<grid, PTG_BLOCK, 0, st>>>(h->P, actions, adtype, io, 1);
+        if (pa13) launch_pdl(k_step<NV, MOD, false, false, (NV == 4 ? 13 : 0)>, grid, st, h->P, actions, adtype, io, 1);
+        else launch_pdl(k_step<NV, MOD, false, false, 0>, grid, st, h->P, actions, adtype, io, 1);
     }
 }
 template <int NV, bool MOD>

@@ -557,6 +557,9 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
     if (P.has_penalty) P.nchg[e] = 0;
 }
 
+#ifndef PTG_PDL
+#define PTG_PDL 1
+#endif
 #ifndef PTG_ORDER
 #define PTG_ORDER 0      // 0: windows staged before the plant transition | 1: transition first, RNG record requested early
 #endif
@@ -737,10 +740,19 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warp_env0 = e - lane;
     const bool use_zig = P.noise_mode == PTG_NOISE_NUMPY;
+#if PTG_PDL
+    // Programmatic dependent launch: the next launch in the stream may become resident as soon as every CTA of this
+    // one has started, so its prologue (ziggurat table staging below) overlaps this kernel's tail wave ...
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
     if (use_zig) {
         zig_kiwi[2 * threadIdx.x] = __ldg(P.zig.ki + threadIdx.x);
         zig_kiwi[2 * threadIdx.x + 1] = (uint64_t)__double_as_longlong(__ldg(P.zig.wi + threadIdx.x));
     }
+#if PTG_PDL
+    // ... and nothing the previous kernel may still be writing (env state, actions) is touched before it completed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     const bool warp_in_range = warp_env0 < n_envs;
     const int nvalid = min(32, n_envs - warp_env0);
     const bool active = e < n_envs;
