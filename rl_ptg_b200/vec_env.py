@@ -189,6 +189,8 @@ class PtGVecEnv(_Base):
         self._tape = None
         self._t_start = time.time()
         self._ev_small = torch.cuda.Event()
+        self._ev_scalars = torch.cuda.Event()
+        self._scalar_off = min(off for name, _, _, off in self.obs_keys if name == "METH_STATUS")
         self.bytes_per_env_step = int(self._L.ptg_bytes_per_env_step(self._h, _TORCH_ACT[act_dtype]))
         if seed is not None:
             self.seed(seed)
@@ -221,10 +223,13 @@ class PtGVecEnv(_Base):
             out[name] = v.view(torch.int32) if is_int else v.view(n, dim)
         return out
 
-    def _obs_numpy(self, buf_h: torch.Tensor, rows=None) -> dict:
+    def _obs_numpy(self, buf_h: torch.Tensor, rows=None, status=None) -> dict:
         views = self._obs_views(buf_h)
         out = {}
         for name, dim, is_int, _ in self.obs_keys:
+            if is_int and status is not None:
+                out[name] = status
+                continue
             a = views[name].numpy()
             if rows is not None:
                 a = a[rows]
@@ -286,7 +291,12 @@ class PtGVecEnv(_Base):
         self._done_h.copy_(self._done, non_blocking=True)
         self._reward_h.copy_(self._reward, non_blocking=True)
         self._ev_small.record(stream)
-        obs_h.copy_(self._obs, non_blocking=True)
+        # the scalar blocks (METH_STATUS first) travel ahead of the two window blocks, so the int64 conversion of
+        # METH_STATUS overlaps the rest of the transfer
+        cut = self._scalar_off
+        obs_h[cut:].copy_(self._obs[cut:], non_blocking=True)
+        self._ev_scalars.record(stream)
+        obs_h[:cut].copy_(self._obs[:cut], non_blocking=True)
         eval_mode = bool(self.cfg.train_or_eval)
         if eval_mode:
             self._info_h.copy_(self._info, non_blocking=True)
@@ -294,6 +304,8 @@ class PtGVecEnv(_Base):
         dones = self._done_h.numpy().view(np.bool_).copy()
         rewards = self._reward_h.numpy().copy()
         any_done = bool(dones.any())
+        self._ev_scalars.synchronize()
+        status = self._obs_views(obs_h)["METH_STATUS"].numpy().astype(np.int64)
         if any_done:
             self._term_obs_h.copy_(self._term_obs, non_blocking=True)
             self._ep_ret_h.copy_(self._ep_ret, non_blocking=True)
@@ -326,7 +338,7 @@ class PtGVecEnv(_Base):
             infos = LazyInfos(self.num_envs, None, make if (eval_mode or any_done) else None)
         else:
             infos = [make(e) for e in range(self.num_envs)]
-        return self._obs_numpy(obs_h), rewards, dones, infos
+        return self._obs_numpy(obs_h, status=status), rewards, dones, infos
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None:

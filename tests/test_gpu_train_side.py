@@ -143,3 +143,55 @@ def test_ppo_rollout_buffers_are_consistent():
     model.learn(model.num_timesteps + 16 * 512)
     assert model.logs and np.isfinite(model.logs[-1]["fps"])
     env.close()
+
+
+def test_postprocessing_matches_reference_info_rows():
+    """Postprocessing.test_performance (src/rl_utils.py:528-565) on the real BS2/OP2 test split, replaying the golden
+    action sequence as the 'policy': the (steps, 24) statistics equal the reference's eval-mode info rows, and the
+    batched device roll-out gives the same columns for every env."""
+    import torch
+    from helpers import golden_kwargs, load_golden
+    from rl_ptg_b200._abi import STATE_NAMES
+    from rl_ptg_b200.postprocessing import Postprocessing, eval_stats_tensor
+    from rl_ptg_b200.vec_env import PtGVecEnv
+    g = load_golden("bs2_op2_eval_test")
+    kw = golden_kwargs("bs2_op2_eval_test")
+    steps = int(kw["eps_sim_steps"])                 # 8640: five steps into the second episode, like the reference
+
+    class Replay:
+        def __init__(self):
+            self.t = 0
+
+        def predict(self, obs, deterministic=True):
+            a = g["actions"][self.t]
+            self.t += 1
+            return a, None
+
+    env = PtGVecEnv(kw, 1, train_or_eval="eval", seed=g["meta"]["seed"])
+    pp = Postprocessing(env, Replay(), steps)
+    pp.test_performance()
+    got = np.stack([pp.stats_dict_test[name] for name in pp.stats_names], axis=1)
+    want = g["infos"][:steps, 0, :].copy()
+    term = g["ints"][:steps, 0, 4].astype(bool)
+    want[term] = 0.0                                  # `if not terminated` leaves those rows zero
+    assert np.allclose(got, want, rtol=1e-9, atol=1e-12)
+    assert list(pp.stats_dict_test) == pp.stats_names and len(pp.stats_names) == 24
+    env.close()
+
+    # batched on the device: 64 envs with the same seed-independent action tape (noise differs per env, prices do not)
+    n = 64
+    envb = PtGVecEnv(kw, n, train_or_eval="eval", seed=g["meta"]["seed"])
+    acts = torch.from_numpy(g["actions"][:steps, 0].astype(np.int64)).to(envb.device)
+    tcount = [0]
+
+    def policy(obs):
+        a = acts[tcount[0]].expand(n)
+        tcount[0] += 1
+        return a
+
+    stats = eval_stats_tensor(envb, policy, 300).cpu().numpy()
+    assert stats.shape == (300, 24, n)
+    assert np.allclose(stats[:, :, 0], want[:300], rtol=1e-9, atol=1e-12)      # env 0 has the golden seed
+    assert np.array_equal(stats[:, 0, :], np.tile(np.arange(300.0)[:, None], (1, n)))   # "step" column
+    assert np.allclose(stats[:, 1, :], stats[:, 1, :1])                        # same prices for every env
+    envb.close()
