@@ -386,11 +386,8 @@ __device__ __forceinline__ Plan plan_transition(int action, uint32_t& meta, int 
     return p;
 }
 
-// EARLY: the RNG record was requested by the caller right after plan_transition (rl); otherwise it is requested here
-template <bool EARLY>
 __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, const Plan& p, int& i, int& j,
-                                                uint32_t& meta, int lut_val, const uint64_t* zig_kiwi,
-                                                const RngLoad& rl) {
+                                                uint32_t& meta, int lut_val, const uint64_t* zig_kiwi) {
     const int S = P.S;
     int state = meta & 7, ds = p.ds, next_state, change = 0;
     if (p.kind == PTG_KIND_CONT) {
@@ -407,7 +404,7 @@ __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, c
         }
         meta = meta_set_tab(meta, state, ds);
         double nz = 0.0;
-        if (P.noise_mode != PTG_NOISE_OFF) nz = EARLY ? draw_noise(P, e, zig_kiwi, rl) : draw_noise(P, e, zig_kiwi, request_rng(P, e));
+        if (P.noise_mode != PTG_NOISE_OFF) nz = draw_noise(P, e, zig_kiwi, request_rng(P, e));
         i = jitter_index(lut_val, nz);
         j = 1;
     } else {                                                                     // _partial / _full

@@ -7,9 +7,9 @@
 //   k_stats_*      deterministic two-stage reduction of finished-episode statistics (warp shuffles)
 //
 // The step kernel is HBM-bound streaming of per-env state + observation rows; the only gathers go to
-// L2-resident tables (step table 80 B/entry, hour row 16*NV B, day row 32 B, clock row 16 B).  The two
-// [n_envs, price_ahead] observation blocks are transposed through shared memory per warp so that every global
-// store is a coalesced 16-byte vector.
+// L2-resident tables (step table 64 B/entry, hour row 16*NV B, day row 32 B, argmin LUT 4 B) and -- on a noise
+// draw -- to the env's 64 B RNG record.  The two [n_envs, price_ahead] observation blocks are transposed through
+// shared memory per warp and leave the SM as one TMA bulk store each.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -560,9 +560,6 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
 #ifndef PTG_PDL
 #define PTG_PDL 1
 #endif
-#ifndef PTG_ORDER
-#define PTG_ORDER 0      // 0: windows staged before the plant transition | 1: transition first, RNG record requested early
-#endif
 #ifndef PTG_STEP_MIN_BLOCKS
 #define PTG_STEP_MIN_BLOCKS 4        // CTAs of 256 threads per SM the step kernel is compiled for (<= 64 registers)
 #endif
@@ -621,12 +618,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         int lut_val = 0;
         if (plan.col >= 0) lut_val = ldg32_nc_keep(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + plan.col);
         const bool draws = plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF;
-        RngLoad rl = {};
-#if PTG_ORDER == 1
-        if (draws) rl = request_rng(P, e);            // both sectors of the RNG record, in flight with everything below
-#else
         if (draws) prefetch_l1(P.rng + e);
-#endif
         // (2) clock of step k+1 (:442-445, integer form of floor(clock_hours), floor(clock_days)) -> market rows of
         //     the NEW hour/day (:446-447) -> observation windows; sin/cos of the clock come from the clock table
         const unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
@@ -635,13 +627,13 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         load_hour_row<NV>(P, t_hour, hrow);
         day = load_day_row(P, t_day);
         const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + (k + 1)));
-#if PTG_ORDER == 0
         stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
         const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
+        // the window tiles go to the TMA before the transition: the fence in front of a bulk store waits for the
+        // thread's outstanding accesses, so it must not sit behind the RNG / step-table requests
         if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
-#endif
-        // (3) plant transition -> step-table entry (2 x 32 B = two sectors)
-        const int ent = apply_transition<PTG_ORDER == 1>(P, e, plan, i, j, meta, lut_val, zig_kiwi, rl);
+        // (3) plant transition (requests the RNG record when it draws) -> step-table entry (2 x 32 B sectors)
+        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi);
         const int state_change = (prev_state != (int)(meta & 7));
         U256 qc, qn;      // qc = {c_gas, c_eua, c_el, c_0}, qn = {norm[6], tinfo, pad}
         if (nvalid == 32) {
@@ -662,12 +654,6 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
             qc = ldg256_nc(P.step_tab + ent);
             qn = ldg256_nc(reinterpret_cast<const char*>(P.step_tab + ent) + 32);
         }
-#if PTG_ORDER == 1
-        // the windows are staged and handed to the TMA while the step-table gather is in flight
-        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
-        const double el = hour_row_el<NV>(hrow);
-        if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
-#endif
         // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
         const double c_gas = __longlong_as_double((long long)qc.a), c_eua = __longlong_as_double((long long)qc.b);
         const double c_el = __longlong_as_double((long long)qc.c), c_0 = __longlong_as_double((long long)qc.d);

@@ -453,6 +453,24 @@ class PtGVecEnv(_Base):
                                          self._stream()))
         return out
 
+    def capture_steps(self, action_buffers: Sequence[torch.Tensor]) -> "torch.cuda.CUDAGraph":
+        """Capture ``len(action_buffers)`` consecutive single steps into ONE CUDA graph (SURVEY.md build plan item 7):
+        ``graph.replay()`` then issues them with a single host call -- for shards small enough that a step (a few us)
+        costs less than a Python/driver launch.  The steps read ``action_buffers[q]`` (fill them before each
+        replay) and leave observation / reward / done of the LAST step in the env's buffers; use
+        ``rollout_tensor`` when every step's outputs are needed."""
+        self._check_open()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):                    # warm-up outside the capture (lazy module loading)
+            self.step_tensor(action_buffers[0])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for a in action_buffers:
+                self.step_tensor(a)
+        return graph
+
     def obs_views_of(self, buf: torch.Tensor) -> dict:
         """Key views of any single obs buffer with this env's layout (e.g. ``rollout['obs'][t]``)."""
         return self._obs_views(buf)

@@ -113,3 +113,23 @@ def test_vec_env_requires_cuda():
     from rl_ptg_b200.vec_env import PtGVecEnv
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         PtGVecEnv(synthetic_kwargs(), 4)
+
+
+def test_lazy_infos_behaves_like_a_list_of_dicts():
+    from rl_ptg_b200.vec_env import LazyInfos
+    made = []
+
+    def make(e):
+        made.append(e)
+        return {"env": e}
+
+    infos = LazyInfos(1_000_000, None, make)
+    assert len(infos) == 1_000_000 and made == []
+    assert infos[5] == {"env": 5} and infos[-1] == {"env": 999_999}
+    infos[5]["extra"] = 1
+    assert infos[5]["extra"] == 1 and made == [5, 999_999]          # identity is stable, nothing else materialised
+    assert [d["env"] for d in infos[10:13]] == [10, 11, 12]
+    with pytest.raises(IndexError):
+        infos[1_000_000]
+    empty = LazyInfos(3)
+    assert list(empty) == [{}, {}, {}]
