@@ -1,1 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4; python tools/microbench.py --steps 1000 2>&1 | grep -v "^$"
+python tools/microbench.py --steps 1000 --no-rollout 2>&1 | grep -v "^$"
+PTG_B200_SO=$PWD/variants/norc.so python tools/microbench.py --steps 1000 --no-rollout 2>&1 | grep -v "^$"
