@@ -327,6 +327,9 @@ def run_ppo_gpu(args):
     from rl_ptg_b200.vec_env import PtGVecEnv
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    if args.ppo_tf32:                      # policy matmuls on the tensor cores (SB3's default is plain fp32)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
     kw = make_kwargs()
     hyper = reference_hyper_kwargs()
     hyper.update(n_steps=args.ppo_n_steps, batch_size=args.ppo_batch, n_epochs=args.ppo_epochs, seed=3654)
@@ -354,7 +357,7 @@ def run_ppo_gpu(args):
            "config": {"workload": "PPO (MultiInputPolicy 2x358 ReLU) on BS2/OP2 mod, GPU VecEnv + VecNormalize + "
                                   "feature rows + GAE on device", "n_envs": args.ppo_envs, "n_steps": args.ppo_n_steps,
                       "batch_size": args.ppo_batch, "n_epochs": args.ppo_epochs,
-                      "collect_env_steps_per_s": steps_done / tc, "collect_share_of_time": tc / dt,
+                      "policy_matmul": "tf32" if args.ppo_tf32 else "fp32", "collect_env_steps_per_s": steps_done / tc, "collect_share_of_time": tc / dt,
                       "baseline_note": "vs_baseline = value / 166.6 env-steps/s, the reference's shipped TensorBoard "
                                        "time/fps (BASELINE.md; unknown hardware, 6 envs)",
                       "episodes_finished": ep["episodes"], "ep_rew_mean": ep["return_mean"]},
@@ -478,6 +481,7 @@ def main():
     ap.add_argument("--ppo-batch", type=int, default=65536)
     ap.add_argument("--ppo-epochs", type=int, default=13)
     ap.add_argument("--ppo-iters", type=int, default=4)
+    ap.add_argument("--ppo-tf32", action="store_true")
     ap.add_argument("--ppo-ref-envs", type=int, default=6)
     ap.add_argument("--ppo-ref-n-steps", type=int, default=4263)
     args = ap.parse_args()

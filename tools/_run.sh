@@ -1,2 +1,2 @@
-python tools/microbench.py --steps 1000 --no-rollout 2>&1 | grep -v "^$"
-PTG_B200_SO=$PWD/variants/norc.so python tools/microbench.py --steps 1000 --no-rollout 2>&1 | grep -v "^$"
+python -m pytest tests/test_gpu_edge_cases.py -m gpu -x -q -k "shard or full_size" 2>&1 | tail -4
+python bench.py --workload ppo --steps 4 --ppo-tf32 2>/dev/null | cut -c1-900
