@@ -215,12 +215,13 @@ void ptg_stats_combine(const PtgEpisodeStats* per_rank, int n_ranks, PtgEpisodeS
  * norm_reward=True, clip_reward=10, gamma=0.99, epsilon=1e-8), split so that the batch moments can be exchanged
  * between ranks (one 24-byte all-gather) before they are folded into the running statistics:
  *   ptg_vecnorm_moments : returns = returns * gamma + reward (VecNormalize._update_reward); moments_out[3] =
- *                         {count, mean, sum of squared deviations} of the new returns (deterministic tree)
+ *                         {count, mean, sum of squared deviations} of the new returns (deterministic tree; one
+ *                         launch; st_in = the current statistics, whose mean is the summation pivot)
  *   ptg_vecnorm_apply   : RunningMeanStd.update_from_moments with `n_batch` such records (training != 0), then
  *                         reward_out = clip(reward_in / sqrt(var + epsilon), +-clip_reward); returns[done] = 0.
  *                         st_in / st_out: {mean, var, count, pad} fp64, distinct buffers (ping-pong). */
-int ptg_vecnorm_moments(PtgHandle* h, const float* reward, double* returns, double gamma, double* moments_out,
-                        void* stream);
+int ptg_vecnorm_moments(PtgHandle* h, const float* reward, double* returns, double gamma, const double* st_in,
+                        double* moments_out, void* stream);
 int ptg_vecnorm_apply(PtgHandle* h, const float* reward_in, const uint8_t* done, double* returns, const double* st_in,
                       double* st_out, const double* moments, int32_t n_batch, int32_t training, double epsilon,
                       double clip_reward, float* reward_out, void* stream);

@@ -57,7 +57,7 @@ def load(build_if_missing: bool = False):
     L.ptg_stats_combine.restype = None
     L.ptg_poll_error.argtypes = [vp, vp]
     f64 = C.c_double
-    L.ptg_vecnorm_moments.argtypes = [vp, vp, vp, f64, vp, vp]
+    L.ptg_vecnorm_moments.argtypes = [vp, vp, vp, f64, vp, vp, vp]
     L.ptg_vecnorm_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, f64, f64, vp, vp]
     L.ptg_features_dim.argtypes = [vp]
     L.ptg_features.argtypes = [vp, vp, vp, vp]

@@ -42,7 +42,8 @@ struct PtgHandle {
     int64_t* d_seeds = nullptr;
     uint8_t* d_mask = nullptr;
     StatAcc* d_partial = nullptr;
-    Moments* d_vn_partial = nullptr;  // per-CTA moments of the VecNormalize returns
+    Sums* d_vn_partial = nullptr;     // per-CTA partial sums of the VecNormalize returns
+    unsigned int* d_vn_ticket = nullptr;
     uint32_t* d_err = nullptr;
     int32_t* d_state_i32 = nullptr;   // scratch for get/set state: 13 int32 arrays
     int64_t* d_state_i64 = nullptr;
@@ -390,6 +391,8 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     PTG_TRY(h->alloc(&h->d_seeds, n)); PTG_TRY(h->alloc(&h->d_mask, n));
     PTG_TRY(h->alloc(&h->d_partial, PTG_STATS_BLOCKS));
     PTG_TRY(h->alloc(&h->d_vn_partial, PTG_STATS_BLOCKS));
+    PTG_TRY(h->alloc(&h->d_vn_ticket, 1));
+    PTG_TRY(cudaMemset(h->d_vn_ticket, 0, sizeof(unsigned int)));
     PTG_TRY(h->alloc(&h->d_state_i32, n * 13)); PTG_TRY(h->alloc(&h->d_state_i64, n)); PTG_TRY(h->alloc(&h->d_state_f64, n * 2));
     P.tape = nullptr; P.tape_len = 0;
     {   // one scheduling wave = resident CTAs of the step kernel on this device
@@ -564,12 +567,15 @@ extern "C" int ptg_episode_stats(PtgHandle* h, PtgEpisodeStats* stats_dev, int c
 // callers either side of the path: VecNormalize (reward), flat policy features, GAE
 // ------------------------------------------------------------------------------------------------------------
 extern "C" int ptg_vecnorm_moments(PtgHandle* h, const float* reward, double* returns, double gamma,
-                                   double* moments_out, void* stream) {
-    if (!h || !reward || !returns || !moments_out) return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
+                                   const double* st_in, double* moments_out, void* stream) {
+    if (!h || !reward || !returns || !st_in || !moments_out) return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
+    if (((uintptr_t)reward & 7) || ((uintptr_t)returns & 15))
+        return fail(PTG_ERR_INVALID_ARGUMENT, "reward must be 8-byte and returns 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    k_vecnorm_returns<<<PTG_STATS_BLOCKS, 256, 0, st>>>(h->P.n_envs, reward, returns, gamma, h->d_vn_partial);
-    k_vecnorm_moments<<<1, 256, 0, st>>>(h->d_vn_partial, PTG_STATS_BLOCKS, reinterpret_cast<Moments*>(moments_out));
-    h->launches += 2;
+    const unsigned grid = (unsigned)std::min<int64_t>(PTG_STATS_BLOCKS, (h->P.n_envs + 511) / 512);
+    k_vecnorm_returns<<<grid, 256, 0, st>>>(h->P.n_envs, reward, returns, gamma, st_in, h->d_vn_partial, h->d_vn_ticket,
+                                            reinterpret_cast<Moments*>(moments_out));
+    h->launches += 1;
     PTG_CUDA(cudaGetLastError());
     return PTG_OK;
 }
@@ -582,7 +588,8 @@ extern "C" int ptg_vecnorm_apply(PtgHandle* h, const float* reward_in, const uin
     if (st_in == st_out) return fail(PTG_ERR_INVALID_ARGUMENT, "st_in and st_out must be distinct buffers");
     if (training && (!moments || n_batch < 1)) return fail(PTG_ERR_INVALID_ARGUMENT, "training needs batch moments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    k_vecnorm_apply<<<blocks_for(h->P.n_envs, 256), 256, 0, st>>>(h->P.n_envs, reward_in, done, returns, st_in, st_out,
+    const unsigned grid = (unsigned)std::min<int64_t>(4 * PTG_STATS_BLOCKS, blocks_for(h->P.n_envs, 256));
+    k_vecnorm_apply<<<grid, 256, 0, st>>>(h->P.n_envs, reward_in, done, returns, st_in, st_out,
                                                                  reinterpret_cast<const Moments*>(moments), n_batch,
                                                                  training, epsilon, clip_reward, reward_out);
     h->launches += 1;

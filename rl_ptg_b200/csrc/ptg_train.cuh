@@ -43,57 +43,114 @@ __device__ __forceinline__ Moments moments_block_reduce(Moments a) {
     return a;   // valid in thread 0
 }
 
-// returns = returns * gamma + reward (VecNormalize._update_reward), per-CTA moments of the new returns.
-// Fixed env -> thread assignment (blocked ranges): the reduction order never depends on timing.
-__global__ void k_vecnorm_returns(int64_t n, const float* __restrict__ reward, double* __restrict__ returns,
-                                  double gamma, Moments* __restrict__ partial) {
-    Moments a{0.0, 0.0, 0.0};
-    const int64_t per_block = (n + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = per_block * blockIdx.x, hi = min(n, lo + per_block);
-    for (int64_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
-        const double r = returns[e] * gamma + (double)reward[e];
-        returns[e] = r;
-        const double n1 = a.n + 1.0, d = r - a.mean;
-        a.mean += d / n1;
-        a.m2 += d * (r - a.mean);
-        a.n = n1;
+// returns = returns * gamma + reward (VecNormalize._update_reward) and the moments of the new returns.
+// Every thread accumulates {count, sum, sum of squares} of (x - pivot) with the SAME pivot (the running mean so far:
+// the returns scatter around it, so there is no cancellation), which makes the partial results plainly additive: the
+// warp / CTA / grid trees are fixed-order additions (bit-reproducible, no divisions), and one thread converts the
+// grand total to {n, mean, M2} at the end.  The LAST CTA to finish (atomic ticket) folds the per-CTA partials, so
+// the whole reduction is one launch.
+struct Sums { double n, s1, s2; };
+__device__ __forceinline__ Sums sums_add(const Sums& a, const Sums& b) { return Sums{a.n + b.n, a.s1 + b.s1, a.s2 + b.s2}; }
+__device__ __forceinline__ Sums sums_block_reduce(Sums a) {
+    __shared__ Sums sm[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        a = sums_add(a, Sums{__shfl_down_sync(0xffffffffu, a.n, o), __shfl_down_sync(0xffffffffu, a.s1, o),
+                             __shfl_down_sync(0xffffffffu, a.s2, o)});
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = a;
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    a = (threadIdx.x < nw) ? sm[threadIdx.x] : Sums{0.0, 0.0, 0.0};
+    if (wid == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            a = sums_add(a, Sums{__shfl_down_sync(0xffffffffu, a.n, o), __shfl_down_sync(0xffffffffu, a.s1, o),
+                                 __shfl_down_sync(0xffffffffu, a.s2, o)});
     }
-    a = moments_block_reduce(a);
-    if (threadIdx.x == 0) partial[blockIdx.x] = a;
+    __syncthreads();
+    return a;   // valid in thread 0
 }
 
-__global__ void k_vecnorm_moments(const Moments* __restrict__ partial, int n_partial, Moments* __restrict__ out) {
-    // sequential per thread over a strided subset, then the fixed tree: deterministic
-    Moments a{0.0, 0.0, 0.0};
-    for (int q = threadIdx.x; q < n_partial; q += blockDim.x) a = moments_combine(a, partial[q]);
-    a = moments_block_reduce(a);
-    if (threadIdx.x == 0) *out = a;
+__global__ void __launch_bounds__(256) k_vecnorm_returns(int64_t n, const float* __restrict__ reward,
+                                                         double* __restrict__ returns, double gamma,
+                                                         const double* __restrict__ st_in, Sums* __restrict__ partial,
+                                                         unsigned int* __restrict__ ticket, Moments* __restrict__ out) {
+    const double pivot = st_in[0];
+    Sums a{0.0, 0.0, 0.0};
+    const int64_t per_block = (((n + gridDim.x - 1) / gridDim.x) + 1) & ~(int64_t)1;      // even: 16 B aligned pairs
+    const int64_t lo = per_block * blockIdx.x, hi = min(n, lo + per_block);
+    for (int64_t e = lo + 2 * threadIdx.x; e < hi; e += 2 * blockDim.x) {
+        if (e + 1 < hi) {
+            double2 r = *reinterpret_cast<const double2*>(returns + e);
+            const float2 w = *reinterpret_cast<const float2*>(reward + e);
+            r.x = r.x * gamma + (double)w.x;
+            r.y = r.y * gamma + (double)w.y;
+            *reinterpret_cast<double2*>(returns + e) = r;
+            const double dx = r.x - pivot, dy = r.y - pivot;
+            a.n += 2.0; a.s1 += dx; a.s1 += dy; a.s2 += dx * dx; a.s2 += dy * dy;
+        } else {
+            const double r = returns[e] * gamma + (double)reward[e];
+            returns[e] = r;
+            const double dx = r - pivot;
+            a.n += 1.0; a.s1 += dx; a.s2 += dx * dx;
+        }
+    }
+    a = sums_block_reduce(a);
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = a;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Sums b{0.0, 0.0, 0.0};            // sequential per thread over a strided subset, then the fixed tree
+    for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
+        const double* pq = reinterpret_cast<const double*>(partial + q);      // other CTAs' results: read at L2
+        b = sums_add(b, Sums{__ldcg(pq), __ldcg(pq + 1), __ldcg(pq + 2)});
+    }
+    b = sums_block_reduce(b);
+    if (threadIdx.x == 0) {
+        const double m = b.n > 0.0 ? b.s1 / b.n : 0.0;
+        *out = Moments{b.n, pivot + m, b.s2 - b.s1 * m};
+        *ticket = 0u;
+    }
 }
 
 // RunningMeanStd.update_from_moments with the batch moments of every rank (rank order), then
 // normalize_reward: clip(reward / sqrt(var + epsilon), -clip, clip); returns[done] = 0.
 // st_in / st_out are distinct buffers ({mean, var, count, pad}): every CTA reads the old statistics, CTA 0 writes the
 // new ones.
-__global__ void k_vecnorm_apply(int64_t n, const float* __restrict__ reward_in, const uint8_t* __restrict__ done,
-                                double* __restrict__ returns, const double* __restrict__ st_in,
-                                double* __restrict__ st_out, const Moments* __restrict__ batch, int n_batch, int training,
-                                double epsilon, double clip, float* __restrict__ reward_out) {
-    double mean = st_in[0], var = st_in[1], count = st_in[2];
-    if (training) {
-        Moments b{0.0, 0.0, 0.0};
-        for (int r = 0; r < n_batch; ++r) b = moments_combine(b, batch[r]);
-        const double batch_var = b.m2 / b.n;                       // np.var (population)
-        const double delta = b.mean - mean, tot = count + b.n;
-        const double new_mean = mean + delta * b.n / tot;
-        const double m_2 = var * count + batch_var * b.n + delta * delta * count * b.n / tot;
-        mean = new_mean; var = m_2 / tot; count = tot;
+__global__ void __launch_bounds__(256) k_vecnorm_apply(int64_t n, const float* __restrict__ reward_in,
+                                                       const uint8_t* __restrict__ done, double* __restrict__ returns,
+                                                       const double* __restrict__ st_in, double* __restrict__ st_out,
+                                                       const Moments* __restrict__ batch, int n_batch, int training,
+                                                       double epsilon, double clip, float* __restrict__ reward_out) {
+    // the statistics update is a few dozen dependent fp64 operations: once per CTA, not once per env
+    __shared__ double s_std;
+    if (threadIdx.x == 0) {
+        double mean = st_in[0], var = st_in[1], count = st_in[2];
+        if (training) {
+            Moments b{0.0, 0.0, 0.0};
+            for (int r = 0; r < n_batch; ++r) b = moments_combine(b, batch[r]);
+            const double batch_var = b.m2 / b.n;                       // np.var (population)
+            const double delta = b.mean - mean, tot = count + b.n;
+            const double new_mean = mean + delta * b.n / tot;
+            const double m_2 = var * count + batch_var * b.n + delta * delta * count * b.n / tot;
+            mean = new_mean; var = m_2 / tot; count = tot;
+        }
+        if (blockIdx.x == 0) { st_out[0] = mean; st_out[1] = var; st_out[2] = count; st_out[3] = 0.0; }
+        s_std = sqrt(var + epsilon);
     }
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e == 0) { st_out[0] = mean; st_out[1] = var; st_out[2] = count; st_out[3] = 0.0; }
-    if (e >= n) return;
-    const double scaled = (double)reward_in[e] / sqrt(var + epsilon);
-    reward_out[e] = (float)fmin(fmax(scaled, -clip), clip);
-    if (done[e]) returns[e] = 0.0;
+    __syncthreads();
+    const double inv_std = 1.0 / s_std;      // (x * (1/s) differs from x / s by <= 1 ulp of fp64: invisible in the fp32 result)
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const double scaled = (double)reward_in[e] * inv_std;
+        reward_out[e] = (float)fmin(fmax(scaled, -clip), clip);
+        if (done[e]) returns[e] = 0.0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -87,8 +87,8 @@ class VecNormalizeReward:
         h, p = self.venv._h, PtGVecEnv._ptr
         moments, n_batch = self._moments, 1
         if self.training:
-            _lib.check(self._L.ptg_vecnorm_moments(h, p(reward), p(self.returns), self.gamma, p(self._moments),
-                                                   self._stream()))
+            _lib.check(self._L.ptg_vecnorm_moments(h, p(reward), p(self.returns), self.gamma, p(self._st[self._cur]),
+                                                   p(self._moments), self._stream()))
             if self.reduce == "global":
                 import torch.distributed as dist
                 if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
