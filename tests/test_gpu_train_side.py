@@ -195,3 +195,49 @@ def test_postprocessing_matches_reference_info_rows():
     assert np.array_equal(stats[:, 0, :], np.tile(np.arange(300.0)[:, None], (1, n)))   # "step" column
     assert np.allclose(stats[:, 1, :], stats[:, 1, :1])                        # same prices for every env
     envb.close()
+
+
+def test_vecnormalize_moment_records_combine_like_one_batch():
+    """reduce="global" without NCCL: two half-batches produce one 24-byte moment record each; folding both records
+    (rank order) into the statistics gives what one batch over all envs gives -- so the reward statistics do not
+    depend on the sharding."""
+    import ctypes as C
+    import torch
+    from rl_ptg_b200 import _lib
+    from rl_ptg_b200.vec_env import PtGVecEnv
+    L = _lib.load()
+    n, dev = 6000, "cuda:0"
+    whole = _env(n)
+    halves = [PtGVecEnv(synthetic_kwargs(dict(scenario=2, operation="OP2")), n // 2, seed=3654, env_id_offset=q * (n // 2),
+                        n_envs_global=n) for q in range(2)]
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    p = PtGVecEnv._ptr
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    st = {k: [torch.tensor([0.0, 1.0, 1e-4, 0.0], dtype=torch.float64, device=dev) for _ in range(2)] for k in "wab"}
+    ret = {"w": torch.zeros(n, dtype=torch.float64, device=dev), "a": torch.zeros(n // 2, dtype=torch.float64, device=dev),
+           "b": torch.zeros(n // 2, dtype=torch.float64, device=dev)}
+    out = {"w": torch.zeros(n, device=dev), "a": torch.zeros(n // 2, device=dev), "b": torch.zeros(n // 2, device=dev)}
+    for env in [whole] + halves:
+        env.reset_tensor()
+    cur = 0
+    for t in range(25):
+        a = torch.randint(0, 5, (n,), generator=g, device=dev)
+        _, rw, dw = whole.step_tensor(a)
+        parts = [h.step_tensor(a[q * (n // 2):(q + 1) * (n // 2)].contiguous()) for q, h in enumerate(halves)]
+        mw = torch.zeros(3, dtype=torch.float64, device=dev)
+        mab = torch.zeros((2, 3), dtype=torch.float64, device=dev)
+        _lib.check(L.ptg_vecnorm_moments(whole._h, p(rw), p(ret["w"]), 0.99, p(st["w"][cur]), p(mw), stream))
+        for q, (h, key) in enumerate(zip(halves, "ab")):
+            _lib.check(L.ptg_vecnorm_moments(h._h, p(parts[q][1]), p(ret[key]), 0.99, p(st[key][cur]), p(mab[q]), stream))
+        _lib.check(L.ptg_vecnorm_apply(whole._h, p(rw), p(dw), p(ret["w"]), p(st["w"][cur]), p(st["w"][cur ^ 1]), p(mw), 1, 1,
+                                       1e-8, 10.0, p(out["w"]), stream))
+        for q, (h, key) in enumerate(zip(halves, "ab")):
+            _lib.check(L.ptg_vecnorm_apply(h._h, p(parts[q][1]), p(parts[q][2]), p(ret[key]), p(st[key][cur]),
+                                           p(st[key][cur ^ 1]), p(mab), 2, 1, 1e-8, 10.0, p(out[key]), stream))
+        cur ^= 1
+        sw, sa, sb = (st[k][cur].cpu().numpy() for k in "wab")
+        assert np.array_equal(sa, sb)                                    # both "ranks" hold identical statistics
+        assert np.allclose(sa[:3], sw[:3], rtol=1e-11, atol=1e-13)
+        assert np.allclose(torch.cat([out["a"], out["b"]]).cpu().numpy(), out["w"].cpu().numpy(), rtol=1e-6, atol=1e-9)
+    for env in [whole] + halves:
+        env.close()
