@@ -333,7 +333,7 @@ def run_ppo_gpu(args):
     kw = make_kwargs()
     hyper = reference_hyper_kwargs()
     hyper.update(n_steps=args.ppo_n_steps, batch_size=args.ppo_batch, n_epochs=args.ppo_epochs, seed=3654)
-    env = PtGVecEnv(kw, args.ppo_envs, seed=3654, device=dev)
+    env = PtGVecEnv(kw, args.ppo_envs, seed=3654, device=dev, obs_layout=args.ppo_layout)
     model = PPO(env, **hyper)
     per_iter = args.ppo_envs * args.ppo_n_steps
     model.learn(per_iter * max(1, args.warmup if args.warmup < 3 else 1))      # warm-up iteration(s): cuBLAS, allocator
@@ -357,7 +357,8 @@ def run_ppo_gpu(args):
            "config": {"workload": "PPO (MultiInputPolicy 2x358 ReLU) on BS2/OP2 mod, GPU VecEnv + VecNormalize + "
                                   "feature rows + GAE on device", "n_envs": args.ppo_envs, "n_steps": args.ppo_n_steps,
                       "batch_size": args.ppo_batch, "n_epochs": args.ppo_epochs,
-                      "policy_matmul": "tf32" if args.ppo_tf32 else "fp32", "collect_env_steps_per_s": steps_done / tc, "collect_share_of_time": tc / dt,
+                      "policy_matmul": "tf32" if args.ppo_tf32 else "fp32", "obs_layout": args.ppo_layout,
+                      "collect_env_steps_per_s": steps_done / tc, "collect_share_of_time": tc / dt,
                       "baseline_note": "vs_baseline = value / 166.6 env-steps/s, the reference's shipped TensorBoard "
                                        "time/fps (BASELINE.md; unknown hardware, 6 envs)",
                       "episodes_finished": ep["episodes"], "ep_rew_mean": ep["return_mean"]},
@@ -482,6 +483,8 @@ def main():
     ap.add_argument("--ppo-epochs", type=int, default=13)
     ap.add_argument("--ppo-iters", type=int, default=4)
     ap.add_argument("--ppo-tf32", action="store_true")
+    ap.add_argument("--ppo-layout", default="flat", choices=["flat", "dict"],
+                    help="flat: the step kernel writes the policy's feature rows | dict: key-major obs + ptg_features")
     ap.add_argument("--ppo-ref-envs", type=int, default=6)
     ap.add_argument("--ppo-ref-n-steps", type=int, default=4263)
     args = ap.parse_args()

@@ -68,6 +68,14 @@ enum PtgScheduleMode {
     PTG_SCHED_SUBPROC = 1  /* SubprocVecEnv: per-env start offset in [0, n_eps_loops), then +1 per reset */
 };
 
+/* Layout of the observation buffers (PtgIO.obs / terminal_obs).
+ *   PTG_OBS_KEY_MAJOR : one contiguous [n_envs, key_dim] block per observation key (the Dict of
+ *                       env/ptg_gym_env.py:222-249 as zero-copy views); METH_STATUS holds int32 bit patterns.
+ *   PTG_OBS_FLAT      : one [ptg_features_dim()]-float row per env in the column order of SB3's CombinedExtractor
+ *                       (see ptg_features): what a MultiInputPolicy consumes, written by the step kernel itself.
+ *                       Built for price_ahead == 13 and train_or_eval = train (else PTG_ERR_UNSUPPORTED). */
+enum PtgObsLayout { PTG_OBS_KEY_MAJOR = 0, PTG_OBS_FLAT = 1 };
+
 /* All scalar knobs the env reads from its constructor dict (src/rl_utils.py:345-403). */
 typedef struct PtgConfig {
     int32_t abi_version;            /* = PTG_ABI_VERSION */
@@ -89,7 +97,7 @@ typedef struct PtgConfig {
     int32_t time1_f_p_f, time2_f_p_f, time23_f_p_f, time3_f_p_f, time34_f_p_f, time4_f_p_f, time45_f_p_f,
             time5_f_p_f;
     int32_t i_fully_developed, j_fully_developed;
-    int32_t _pad0;
+    int32_t obs_layout;             /* PtgObsLayout: 0 = key-major blocks (default), 1 = flat feature rows */
     double noise;                   /* sigma [rows] */
     double eps_len_d;               /* [d] */
     double state_change_penalty;
@@ -136,7 +144,8 @@ typedef struct PtgObsKey {
     char name[24];
     int32_t dim;             /* values per env */
     int32_t is_int32;        /* 1 for METH_STATUS */
-    int64_t offset;          /* element offset of the [n_envs, dim] block inside obs */
+    int64_t offset;          /* key-major: element offset of the [n_envs, dim] block inside obs;
+                                flat: first column of the key inside a row (METH_STATUS: 6 one-hot floats) */
 } PtgObsKey;
 
 /* Episode statistics of finished episodes since the last clear (per rank; combine across ranks with

@@ -23,6 +23,7 @@ STATE_NAMES = ("standby", "cooldown", "startup", "partial_load", "full_load")   
 ACT_I64, ACT_I32, ACT_U8, ACT_F32 = 0, 1, 2, 3
 NOISE_NUMPY, NOISE_TAPE, NOISE_OFF = 0, 1, 2
 SCHED_DUMMY, SCHED_SUBPROC = 0, 1
+OBS_KEY_MAJOR, OBS_FLAT = 0, 1
 
 PTG_OK = 0
 STATUS_NAMES = {0: "PTG_OK", -1: "PTG_ERR_INVALID_ARGUMENT", -2: "PTG_ERR_CUDA", -3: "PTG_ERR_UNSUPPORTED",
@@ -44,7 +45,7 @@ _I32_FIELDS = (
     "time5_p_f_p",
     "time1_f_p_f", "time2_f_p_f", "time23_f_p_f", "time3_f_p_f", "time34_f_p_f", "time4_f_p_f", "time45_f_p_f",
     "time5_f_p_f",
-    "i_fully_developed", "j_fully_developed", "_pad0",
+    "i_fully_developed", "j_fully_developed", "obs_layout",
 )
 _F64_FIELDS = (
     "noise", "eps_len_d", "state_change_penalty", "reward_level",
@@ -119,7 +120,7 @@ def _as_int(name: str, v) -> int:
 
 
 def config_from_kwargs(dict_input: dict, train_or_eval: str = "train", noise_mode: int = NOISE_NUMPY,
-                       schedule_mode: int | None = None) -> PtgConfig:
+                       schedule_mode: int | None = None, obs_layout: int = 0) -> PtgConfig:
     """Validate the reference constructor dict and pack its scalars."""
     d = dict_input
     if train_or_eval not in ("train", "eval"):
@@ -146,6 +147,7 @@ def config_from_kwargs(dict_input: dict, train_or_eval: str = "train", noise_mod
     if schedule_mode is None:
         schedule_mode = SCHED_SUBPROC if d.get("parallel") == "Multiprocessing" else SCHED_DUMMY
     cfg.schedule_mode = schedule_mode
+    cfg.obs_layout = int(obs_layout)
     cfg.n_eps_loops = max(1, int(d.get("n_eps_loops", 1) or 1))
     for k in _TIME_KEYS:
         setattr(cfg, k, _as_int(k, d[k]))

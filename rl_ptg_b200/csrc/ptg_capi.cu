@@ -100,19 +100,24 @@ void launch_step_t(PtgHandle* h, const void* actions, int adtype, const PtgIO& i
     const unsigned grid = blocks_for(h->P.n_envs, PTG_BLOCK);
     h->P.action_bytes = adtype == PTG_ACT_I64 ? 8 : adtype == PTG_ACT_U8 ? 1 : 4;
     const bool pa13 = NV == 4 && h->P.pa == 13;       // compile-time price_ahead for the reference default
-    if (T > 0) {
-        if (pa13) launch_pdl(k_step<NV, MOD, true, false, (NV == 4 ? 13 : 0)>, grid, st, h->P, actions, adtype, io, T);
+    constexpr int P13 = NV == 4 ? 13 : 0;
+    if (h->P.flat) {                                  // (validated at create: price_ahead == 13, train mode)
+        if (T > 0) launch_pdl(k_step<4, MOD, true, false, 13, true>, grid, st, h->P, actions, adtype, io, T);
+        else launch_pdl(k_step<4, MOD, false, false, 13, true>, grid, st, h->P, actions, adtype, io, 1);
+    } else if (T > 0) {
+        if (pa13) launch_pdl(k_step<NV, MOD, true, false, P13>, grid, st, h->P, actions, adtype, io, T);
         else launch_pdl(k_step<NV, MOD, true, false, 0>, grid, st, h->P, actions, adtype, io, T);
     } else if (h->P.eval_mode && io.info) {
         launch_pdl(k_step<NV, MOD, false, true, 0>, grid, st, h->P, actions, adtype, io, 1);
     } else {
-        if (pa13) launch_pdl(k_step<NV, MOD, false, false, (NV == 4 ? 13 : 0)>, grid, st, h->P, actions, adtype, io, 1);
+        if (pa13) launch_pdl(k_step<NV, MOD, false, false, P13>, grid, st, h->P, actions, adtype, io, 1);
         else launch_pdl(k_step<NV, MOD, false, false, 0>, grid, st, h->P, actions, adtype, io, 1);
     }
 }
 template <int NV, bool MOD>
 void launch_reset_t(PtgHandle* h, const int64_t* seeds, const uint8_t* mask, const PtgIO& io, cudaStream_t st) {
-    k_reset<NV, MOD><<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, 0, st>>>(h->P, seeds, mask, io);
+    if (h->P.flat) k_reset<4, MOD, true><<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, 0, st>>>(h->P, seeds, mask, io);
+    else k_reset<NV, MOD><<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, 0, st>>>(h->P, seeds, mask, io);
 }
 
 #define PTG_DISPATCH(fn, ...)                                                     \
@@ -135,6 +140,9 @@ int validate(const PtgConfig* c, const PtgTables* t, int64_t n_envs, int64_t off
     if (c->action_type != 0 && c->action_type != 1) return fail(PTG_ERR_INVALID_ARGUMENT, "action_type must be discrete(0) or continuous(1)");
     if (c->train_or_eval != 0 && c->train_or_eval != 1) return fail(PTG_ERR_INVALID_ARGUMENT, "train_or_eval must be train(0) or eval(1)");
     if (c->noise_mode < 0 || c->noise_mode > 2) return fail(PTG_ERR_INVALID_ARGUMENT, "noise_mode out of range");
+    if (c->obs_layout != PTG_OBS_KEY_MAJOR && c->obs_layout != PTG_OBS_FLAT) return fail(PTG_ERR_INVALID_ARGUMENT, "obs_layout out of range");
+    if (c->obs_layout == PTG_OBS_FLAT && (c->price_ahead != 13 || c->train_or_eval != 0))
+        return fail(PTG_ERR_UNSUPPORTED, "the flat observation layout is built for price_ahead == 13 and train_or_eval = train");
     if (c->schedule_mode < 0 || c->schedule_mode > 1) return fail(PTG_ERR_INVALID_ARGUMENT, "schedule_mode out of range");
     if (c->price_ahead < 1) return fail(PTG_ERR_INVALID_ARGUMENT, "price_ahead must be >= 1");
     if (c->price_ahead > PTG_MAX_PRICE_AHEAD) return fail(PTG_ERR_UNSUPPORTED, "price_ahead > 16 is not supported by the packed hour row");
@@ -219,31 +227,50 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     B.rc = R;
     for (int q = 0; q < 6; ++q) P.prob_thre[q] = -1 + q * ((1.0 - (-1.0)) / 5);   // :151-155
 
-    // ---- observation layout: key-major blocks, each block start 16 B aligned ----
+    // ---- observation layout ----
     P.n_pad = round_up4(n_envs);
-    int64_t off = 0;
-    auto add_key = [&](const char* name, int dim, int is_int, int64_t elems) {
+    P.flat = c.obs_layout == PTG_OBS_FLAT;
+    auto push_key = [&](const char* name, int dim, int is_int, int64_t offset) {
         PtgObsKey k{};
         std::snprintf(k.name, sizeof(k.name), "%s", name);
-        k.dim = dim; k.is_int32 = is_int; k.offset = off;
+        k.dim = dim; k.is_int32 = is_int; k.offset = offset;
         h->keys.push_back(k);
-        off += round_up4(elems);
     };
-    P.off_win0 = off;
-    if (P.raw) {
-        add_key("Elec_Price", P.pa, 0, n_envs * P.pa);
-        P.off_win1 = 0;
-        P.off_gas = off; add_key("Gas_Price", 2, 0, n_envs * 2);
-        P.off_eua = off; add_key("EUA_Price", 2, 0, n_envs * 2);
-    } else {
-        add_key("Pot_Reward", P.pa, 0, n_envs * P.pa);
-        P.off_win1 = off; add_key("Part_Full", P.pa, 0, n_envs * P.pa);
+    if (P.flat) {      // one feature row per env, keys = columns in CombinedExtractor order (see ptg_features)
+        const int pa = P.pa;
+        int col = 0;
+        auto col_key = [&](const char* name, int dim) { push_key(name, dim, 0, col); col += dim; };
+        col_key("CH4_syn_MolarFlow", 1);
+        if (P.raw) { col_key("EUA_Price", 2); col_key("Elec_Heating", 1); col_key("Elec_Price", pa); col_key("Gas_Price", 2); }
+        else col_key("Elec_Heating", 1);
+        col_key("H2O_DE_MassFlow", 1); col_key("H2_in_MolarFlow", 1); col_key("H2_res_MolarFlow", 1);
+        col_key("METH_STATUS", 6);
+        if (!P.raw) { col_key("Part_Full", pa); col_key("Pot_Reward", pa); }
+        col_key("T_CAT", 1); col_key("Temp_hour_enc_cos", 1); col_key("Temp_hour_enc_sin", 1);
+        P.off_win0 = P.off_win1 = P.off_gas = P.off_eua = P.off_scalar = 0;
+        P.obs_elems = round_up4(n_envs * col);
+    } else {           // key-major blocks, each block start 16 B aligned
+        int64_t off = 0;
+        auto add_key = [&](const char* name, int dim, int is_int, int64_t elems) {
+            push_key(name, dim, is_int, off);
+            off += round_up4(elems);
+        };
+        P.off_win0 = off;
+        if (P.raw) {
+            add_key("Elec_Price", P.pa, 0, n_envs * P.pa);
+            P.off_win1 = 0;
+            P.off_gas = off; add_key("Gas_Price", 2, 0, n_envs * 2);
+            P.off_eua = off; add_key("EUA_Price", 2, 0, n_envs * 2);
+        } else {
+            add_key("Pot_Reward", P.pa, 0, n_envs * P.pa);
+            P.off_win1 = off; add_key("Part_Full", P.pa, 0, n_envs * P.pa);
+        }
+        P.off_scalar = off;
+        const char* scalar_names[9] = {"METH_STATUS", "T_CAT", "H2_in_MolarFlow", "CH4_syn_MolarFlow", "H2_res_MolarFlow",
+                                       "H2O_DE_MassFlow", "Elec_Heating", "Temp_hour_enc_sin", "Temp_hour_enc_cos"};
+        for (int q = 0; q < 9; ++q) add_key(scalar_names[q], 1, q == 0, n_envs);
+        P.obs_elems = off;
     }
-    P.off_scalar = off;
-    const char* scalar_names[9] = {"METH_STATUS", "T_CAT", "H2_in_MolarFlow", "CH4_syn_MolarFlow", "H2_res_MolarFlow",
-                                   "H2O_DE_MassFlow", "Elec_Heating", "Temp_hour_enc_sin", "Temp_hour_enc_cos"};
-    for (int q = 0; q < 9; ++q) add_key(scalar_names[q], 1, q == 0, n_envs);
-    P.obs_elems = off;
 
     // ---- upload raw tables ----
     int32_t ent = 0;
@@ -604,6 +631,7 @@ extern "C" int ptg_features_dim(const PtgHandle* h) {
 
 extern "C" int ptg_features(PtgHandle* h, const float* obs, float* feat, void* stream) {
     if (!h || !obs || !feat) return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
+    if (h->P.flat) return fail(PTG_ERR_INVALID_ARGUMENT, "the env already writes flat feature rows (obs_layout = flat)");
     const int F = ptg_features_dim(h);
     k_features<<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, (size_t)(PTG_BLOCK * F) * sizeof(float),
                  static_cast<cudaStream_t>(stream)>>>(h->P, obs, feat, F);
@@ -669,7 +697,8 @@ extern "C" int64_t ptg_bytes_per_env_step(const PtgHandle* h, int action_dtype) 
     if (!h) return 0;
     const int64_t act = action_dtype == PTG_ACT_I64 ? 8 : action_dtype == PTG_ACT_U8 ? 1 : 4;
     const int64_t state_rd = 16 + 4 + 8 + 8, state_wr = 16 + 4 + 8;
-    return act + state_rd + state_wr + 4 * (int64_t)h->P.obs_dim + 4 + 1;
+    const int64_t obs_floats = h->P.flat ? ptg_features_dim(h) : h->P.obs_dim;
+    return act + state_rd + state_wr + 4 * obs_floats + 4 + 1;
 }
 
 extern "C" int ptg_kernel_launches(const PtgHandle* h, int64_t* out) {

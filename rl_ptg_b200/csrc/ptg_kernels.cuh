@@ -348,6 +348,77 @@ __device__ __noinline__ void emit_obs_scalar(const DevParams& P, float* __restri
     sc[8 * P.n_pad] = c.cos_h;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// flat observation layout (PtgConfig.obs_layout == 1, price_ahead == 13): one [F]-float feature row per env in the
+// column order of SB3's CombinedExtractor (ptg_features), written by the step kernel itself
+//   mod (F = 40): CH4, heat, H2O, H2_in, H2_res | one-hot(status)[6] | Part_Full[13] | Pot_Reward[13] | T, cos, sin
+//   raw (F = 31): CH4 | EUA[2] | heat | Elec_Price[13] | Gas[2] | H2O, H2_in, H2_res | one-hot[6] | T, cos, sin
+// ------------------------------------------------------------------------------------------------------------
+#define PTG_FLAT_F(MOD) ((MOD) ? 40 : 31)
+
+// Cold path: one env's row with plain stores from re-read tables (reset kernel, terminal observations).
+template <bool MOD>
+__device__ __noinline__ void emit_flat_row(const DevParams& P, float* __restrict__ obs, int64_t e, ObsKey key) {
+    float* r = obs + e * PTG_FLAT_F(MOD);
+    const float* w = reinterpret_cast<const float*>(P.hour_tab + (int64_t)key.t_hour * 4);
+    float nrm[6];
+    for (int q = 0; q < 6; ++q) nrm[q] = key.ent >= 0 ? P.step_tab[key.ent].norm[q] : P.reset_norm[q];
+    const ClockRow c = P.clock_tab[key.k1];
+    int oh;
+    if (MOD) {
+        r[0] = nrm[2]; r[1] = nrm[5]; r[2] = nrm[4]; r[3] = nrm[1]; r[4] = nrm[3]; oh = 5;
+        const int bits = __float_as_int(w[13]);
+        for (int a = 0; a < 13; ++a) { r[11 + a] = (float)((bits << (30 - 2 * a)) >> 30); r[24 + a] = w[a]; }
+        r[37] = nrm[0]; r[38] = c.cos_h; r[39] = c.sin_h;
+    } else {
+        const DayRow day = P.day_tab[key.t_day];
+        r[0] = nrm[2]; r[1] = day.eua_n0; r[2] = day.eua_n1; r[3] = nrm[5];
+        for (int a = 0; a < 13; ++a) r[4 + a] = w[a];
+        r[17] = day.gas_n0; r[18] = day.gas_n1; r[19] = nrm[4]; r[20] = nrm[1]; r[21] = nrm[3]; oh = 22;
+        r[28] = nrm[0]; r[29] = c.cos_h; r[30] = c.sin_h;
+    }
+    for (int q = 0; q < 6; ++q) r[oh + q] = key.status == q ? 1.0f : 0.0f;
+}
+
+// Hot path, early half: everything of the row that only needs the market rows.  mod: six 16-byte groups (Part_Full
+// 1..12, Pot_Reward 0..11) as STS.128 (row stride 160 B: 2-way conflicts, 6 instructions instead of 24); the two
+// window values that share a group with late scalars are returned.  raw: 17 conflict-free scalar stores (stride 31).
+template <bool MOD>
+__device__ __forceinline__ void stage_flat_early(float* row, const float4 (&h)[4], const DayRow& day, float& pf0, float& pr12) {
+    if (MOD) {
+        const int bits = __float_as_int(h[3].y);
+        auto pf = [bits](int a) { return (float)((bits << (30 - 2 * a)) >> 30); };
+        float4* r4 = reinterpret_cast<float4*>(row);
+        r4[3] = make_float4(pf(1), pf(2), pf(3), pf(4));
+        r4[4] = make_float4(pf(5), pf(6), pf(7), pf(8));
+        r4[5] = make_float4(pf(9), pf(10), pf(11), pf(12));
+        r4[6] = h[0]; r4[7] = h[1]; r4[8] = h[2];
+        pf0 = pf(0); pr12 = h[3].x;
+    } else {
+        row[1] = day.eua_n0; row[2] = day.eua_n1;
+        row[4] = h[0].x; row[5] = h[0].y; row[6] = h[0].z; row[7] = h[0].w; row[8] = h[1].x; row[9] = h[1].y;
+        row[10] = h[1].z; row[11] = h[1].w; row[12] = h[2].x; row[13] = h[2].y; row[14] = h[2].z; row[15] = h[2].w;
+        row[16] = h[3].x; row[17] = day.gas_n0; row[18] = day.gas_n1;
+    }
+}
+// late half: plant scalars, one-hot status, clock
+template <bool MOD>
+__device__ __forceinline__ void stage_flat_late(float* row, const ObsRegs& o, float pf0, float pr12) {
+    const int s = o.status;
+    if (MOD) {
+        float4* r4 = reinterpret_cast<float4*>(row);
+        r4[0] = make_float4(o.norm[2], o.norm[5], o.norm[4], o.norm[1]);
+        r4[1] = make_float4(o.norm[3], s == 0 ? 1.f : 0.f, s == 1 ? 1.f : 0.f, s == 2 ? 1.f : 0.f);
+        r4[2] = make_float4(s == 3 ? 1.f : 0.f, s == 4 ? 1.f : 0.f, s == 5 ? 1.f : 0.f, pf0);
+        r4[9] = make_float4(pr12, o.norm[0], o.cos_h, o.sin_h);
+    } else {
+        row[0] = o.norm[2]; row[3] = o.norm[5]; row[19] = o.norm[4]; row[20] = o.norm[1]; row[21] = o.norm[3];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) row[22 + q] = s == q ? 1.f : 0.f;
+        row[28] = o.norm[0]; row[29] = o.cos_h; row[30] = o.sin_h;
+    }
+}
+
 __device__ __forceinline__ float4 f4_lo(unsigned long long a, unsigned long long b) {
     return make_float4(__uint_as_float((uint32_t)a), __uint_as_float((uint32_t)(a >> 32)), __uint_as_float((uint32_t)b),
                        __uint_as_float((uint32_t)(b >> 32)));
@@ -478,7 +549,7 @@ __global__ void k_construct(const __grid_constant__ DevParams P) {
     P.fin_min[e] = INFINITY; P.fin_max[e] = -INFINITY;
 }
 
-template <int NV, bool MOD>
+template <int NV, bool MOD, bool FLAT = false>
 __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ DevParams P, const int64_t* seeds,
                                                      const uint8_t* mask, const __grid_constant__ PtgIO io) {
     __shared__ __align__(128) float stage[PTG_BLOCK / 32][2 * PTG_STAGE_FLOATS(NV)];
@@ -519,7 +590,8 @@ __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ Dev
         o.sin_h = 0.0f; o.cos_h = 1.0f;                   // math.sin(0), math.cos(0), :102-103
     }
     if (io.obs != nullptr) {
-        if (mask == nullptr) emit_obs<NV, MOD>(P, io.obs, stage[wid], e, active, lane, warp_env0, nvalid, hrow, day, o);
+        if (FLAT) { if (doit) emit_flat_row<MOD>(P, io.obs, e, ObsKey{-1, t_hour, t_day, PTG_COOLDOWN, 0}); }
+        else if (mask == nullptr) emit_obs<NV, MOD>(P, io.obs, stage[wid], e, active, lane, warp_env0, nvalid, hrow, day, o);
         else if (doit) emit_obs_scalar<NV, MOD>(P, io.obs, e, ObsKey{-1, t_hour, t_day, PTG_COOLDOWN, 0});
     }
     if (lane == 0) tma_store_wait_read();
@@ -533,11 +605,14 @@ __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ Dev
 // ------------------------------------------------------------------------------------------------------------
 // End of an episode (rare): record the terminal observation and the Monitor record, fold the episode into the
 // finished-episode accumulators and write the reset state (next entry of the episode schedule) to global memory.
-template <int NV, bool MOD>
+template <int NV, bool MOD, bool FLAT = false>
 __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io, int64_t e, bool record, int k,
                                             double ep_ret, int cur_action, ObsKey key) {
     if (record) {
-        if (io.terminal_obs != nullptr) emit_obs_scalar<NV, MOD>(P, io.terminal_obs, e, key);
+        if (io.terminal_obs != nullptr) {
+            if (FLAT) emit_flat_row<MOD>(P, io.terminal_obs, e, key);
+            else emit_obs_scalar<NV, MOD>(P, io.terminal_obs, e, key);
+        }
         if (io.episode_return != nullptr) io.episode_return[e] = ep_ret;
         if (io.episode_length != nullptr) io.episode_length[e] = k;
     }
@@ -589,6 +664,27 @@ __device__ __forceinline__ int decode_action_raw(const DevParams& P, long long r
     return act;
 }
 
+// Step-table gather (one 64 B entry per env).  L1TEX cost of a gather is per (instruction, 128 B line): in a full
+// warp a lane PAIR splits its two entries so that each LDG.256 touches 16 lines instead of 32 (even lane: first
+// halves, odd lane: second halves), then the halves are exchanged with four 64-bit shuffles.
+__device__ __forceinline__ void gather_step_entry(const DevParams& P, int ent, int lane, int nvalid, U256& qc, U256& qn) {
+    if (nvalid == 32) {
+        const int ent_p = __shfl_xor_sync(0xffffffffu, ent, 1);
+        const bool odd = lane & 1;
+        const char* base = reinterpret_cast<const char*>(P.step_tab) + (odd ? 32 : 0);
+        const U256 a = ldg256_nc(base + (int64_t)(odd ? ent_p : ent) * 64);     // the even lane's entry
+        const U256 b = ldg256_nc(base + (int64_t)(odd ? ent : ent_p) * 64);     // the odd lane's entry
+        U256 snd = odd ? a : b, rcv;
+        rcv.a = __shfl_xor_sync(0xffffffffu, snd.a, 1); rcv.b = __shfl_xor_sync(0xffffffffu, snd.b, 1);
+        rcv.c = __shfl_xor_sync(0xffffffffu, snd.c, 1); rcv.d = __shfl_xor_sync(0xffffffffu, snd.d, 1);
+        qc = odd ? rcv : a;
+        qn = odd ? b : rcv;
+    } else {
+        qc = ldg256_nc(P.step_tab + ent);
+        qn = ldg256_nc(reinterpret_cast<const char*>(P.step_tab + ent) + 32);
+    }
+}
+
 // One env step of one thread.  Ordering (each group only depends on the ones above it):
 //   1. argmin-LUT gather + prefetch of the RNG line      <- only needs (state, action)
 //   2. clock row -> market rows -> stage the two observation windows in shared memory (independent of the
@@ -636,24 +732,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi);
         const int state_change = (prev_state != (int)(meta & 7));
         U256 qc, qn;      // qc = {c_gas, c_eua, c_el, c_0}, qn = {norm[6], tinfo, pad}
-        if (nvalid == 32) {
-            // L1TEX cost of a gather is per (instruction, 128 B line): a lane pair splits its two entries so that
-            // each LDG.256 touches 16 lines instead of 32 (even lane: first halves, odd lane: second halves), then
-            // the halves are exchanged with four 64-bit shuffles
-            const int ent_p = __shfl_xor_sync(0xffffffffu, ent, 1);
-            const bool odd = lane & 1;
-            const char* base = reinterpret_cast<const char*>(P.step_tab) + (odd ? 32 : 0);
-            const U256 a = ldg256_nc(base + (int64_t)(odd ? ent_p : ent) * 64);     // the even lane's entry
-            const U256 b = ldg256_nc(base + (int64_t)(odd ? ent : ent_p) * 64);     // the odd lane's entry
-            U256 snd = odd ? a : b, rcv;
-            rcv.a = __shfl_xor_sync(0xffffffffu, snd.a, 1); rcv.b = __shfl_xor_sync(0xffffffffu, snd.b, 1);
-            rcv.c = __shfl_xor_sync(0xffffffffu, snd.c, 1); rcv.d = __shfl_xor_sync(0xffffffffu, snd.d, 1);
-            qc = odd ? rcv : a;
-            qn = odd ? b : rcv;
-        } else {
-            qc = ldg256_nc(P.step_tab + ent);
-            qn = ldg256_nc(reinterpret_cast<const char*>(P.step_tab + ent) + 32);
-        }
+        gather_step_entry(P, ent, lane, nvalid, qc, qn);
         // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
         const double c_gas = __longlong_as_double((long long)qc.a), c_eua = __longlong_as_double((long long)qc.b);
         const double c_el = __longlong_as_double((long long)qc.c), c_0 = __longlong_as_double((long long)qc.d);
@@ -712,13 +791,99 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
     }
 }
 
+// One env step with the flat observation layout: the same transition / reward path as step_one, but the whole
+// observation of a warp -- 32 rows of F floats, contiguous in the output -- is assembled in shared memory and leaves
+// the SM as ONE bulk store (5 120 B for mod) at the end of the step; no scalar observation stores at all.
+template <bool MOD>
+__device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& io, long long action_raw, int adtype,
+                                              bool single, int e, bool active, int lane, int warp_env0, int nvalid,
+                                              float* sm, const uint64_t* zig_kiwi, float* __restrict__ obs_out,
+                                              float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int& i,
+                                              int& j, int& k, uint32_t& meta, int32_t& tinfo, int2& ep, double& ep_ret) {
+    constexpr int F = PTG_FLAT_F(MOD);
+    float4 hrow[4];
+    DayRow day;
+    ObsRegs o;
+    float reward = 0.f, pf0 = 0.f, pr12 = 0.f;
+    const int done = active && (k == P.eps_sim_steps - 6);
+    float* row = sm + lane * F;
+    if (lane == 0) tma_store_wait_read();         // the previous step's bulk store (rollout kernel) is done with the tile
+    __syncwarp();
+    if (active) {
+        const int action = decode_action_raw(P, action_raw, adtype, (meta >> 4) & 7);
+        const int prev_state = meta & 7;
+        const Plan plan = plan_transition(action, meta, tinfo & 7);
+        int lut_val = 0;
+        if (plan.col >= 0) lut_val = ldg32_nc_keep(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + plan.col);
+        if (plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF) prefetch_l1(P.rng + e);
+        const unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
+        int t_hour = ep.x + (int)(sec / 3600u), t_day = ep.y + (int)(sec / 86400u);
+        clamp_market_index(P, t_hour, t_day);
+        load_hour_row<4>(P, t_hour, hrow);
+        day = load_day_row(P, t_day);
+        const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + (k + 1)));
+        stage_flat_early<MOD>(row, hrow, day, pf0, pr12);
+        const double el = hour_row_el<4>(hrow);
+        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi);
+        const int state_change = (prev_state != (int)(meta & 7));
+        U256 qc, qn;
+        gather_step_entry(P, ent, lane, nvalid, qc, qn);
+        const double c_gas = __longlong_as_double((long long)qc.a), c_eua = __longlong_as_double((long long)qc.b);
+        const double c_el = __longlong_as_double((long long)qc.c), c_0 = __longlong_as_double((long long)qc.d);
+        double rew = __fma_rn(c_gas, day.gas, __fma_rn(c_eua, day.eua, __fma_rn(-c_el, el, c_0)));
+        if (state_change) rew -= P.penalty;
+        ep_ret += rew;
+        reward = (float)rew;
+        o.norm[0] = __uint_as_float((uint32_t)qn.a); o.norm[1] = __uint_as_float((uint32_t)(qn.a >> 32));
+        o.norm[2] = __uint_as_float((uint32_t)qn.b); o.norm[3] = __uint_as_float((uint32_t)(qn.b >> 32));
+        o.norm[4] = __uint_as_float((uint32_t)qn.c); o.norm[5] = __uint_as_float((uint32_t)(qn.c >> 32));
+        tinfo = (int32_t)(uint32_t)qn.d;
+        o.status = meta & 7;
+        o.sin_h = sc2.x; o.cos_h = sc2.y;
+        if (P.has_penalty) P.nchg[e] += (uint32_t)state_change;
+        k += 1;
+        if (done) {                                   // SB3 auto-reset: the returned row is the reset observation
+            finish_episode<4, MOD, true>(P, io, e, single, k, ep_ret, (meta >> 4) & 7,
+                                         ObsKey{ent, t_hour, t_day, (int)(meta & 7), k});
+            const int4 core = P.core[e];
+            tinfo = P.tinfo[e]; ep = P.ep[e];
+            i = core.x; j = core.y; k = core.z; meta = (uint32_t)core.w; ep_ret = 0.0;
+            t_hour = ep.x; t_day = ep.y;
+            clamp_market_index(P, t_hour, t_day);
+            load_hour_row<4>(P, t_hour, hrow);
+            day = load_day_row(P, t_day);
+            stage_flat_early<MOD>(row, hrow, day, pf0, pr12);
+            o.status = PTG_COOLDOWN;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) o.norm[q] = P.reset_norm[q];
+            o.sin_h = 0.0f; o.cos_h = 1.0f;
+        }
+        stage_flat_late<MOD>(row, o, pf0, pr12);
+    }
+    float* g = obs_out + (int64_t)warp_env0 * F;
+    const uint32_t bytes = (uint32_t)(nvalid * F) * 4u;
+    if ((bytes & 15u) == 0) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_1d(g, sm, bytes); tma_store_commit(); }
+    } else {                                          // ragged tail of the raw design: plain stores
+        __syncwarp();
+        for (int idx = lane; idx < nvalid * F; idx += 32) g[idx] = sm[idx];
+    }
+    if (active) {
+        st_stream(rew_out + e, reward);
+        st_stream(done_out + e, (uint8_t)done);
+    }
+}
+
 // VecEnv.step_wait(): MANY = false -> exactly one step (ptg_step); MANY = true -> T steps with the plant state
 // kept in registers between steps (ptg_step_many).  EVAL = the 24-field info of train_or_eval == "eval".
-template <int NV, bool MOD, bool MANY, bool EVAL, int PAC>
+template <int NV, bool MOD, bool MANY, bool EVAL, int PAC, bool FLAT = false>
 __global__ void __launch_bounds__(PTG_BLOCK, PTG_STEP_MIN_BLOCKS)
 k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, int adtype,
        const __grid_constant__ PtgIO io, int T) {
-    __shared__ __align__(128) float stage[PTG_BLOCK / 32][2 * PTG_STAGE_FLOATS(NV)];
+    static_assert(!FLAT || (NV == 4 && PAC == 13 && !EVAL), "the flat layout is built for price_ahead == 13");
+    __shared__ __align__(128) float stage[PTG_BLOCK / 32][FLAT ? 32 * PTG_FLAT_F(MOD) : 2 * PTG_STAGE_FLOATS(NV)];
     __shared__ __align__(16) uint64_t zig_kiwi[2 * 256];   // {ki, wi} of numpy's ziggurat: 4 KB, one LDS.128 per draw
     static_assert(PTG_BLOCK == 256, "one ziggurat layer per thread");
     const int n_envs = (int)P.n_envs;                   // < 2^26 (checked by ptg_create): 32-bit index arithmetic
@@ -764,18 +929,23 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
         }
     }
 
+    const uint64_t* zig = use_zig ? zig_kiwi : nullptr;
     if (!MANY) {
-        step_one<NV, MOD, EVAL, PAC>(P, io, action_raw, adtype, true, e, active, lane, warp_env0, nvalid, stage[wid],
-                                     use_zig ? zig_kiwi : nullptr,
+        if (FLAT) step_one_flat<MOD>(P, io, action_raw, adtype, true, e, active, lane, warp_env0, nvalid, stage[wid], zig,
                                      io.obs, io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
+        else step_one<NV, MOD, EVAL, PAC>(P, io, action_raw, adtype, true, e, active, lane, warp_env0, nvalid, stage[wid],
+                                          zig, io.obs, io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
     } else {
         for (int t = 0; t < T; ++t) {
             const long long a_now = action_raw;
             if (t + 1 < T) action_raw = load_action_raw(actions, adtype, (int64_t)(t + 1) * n_envs + le);   // next step's
-            step_one<NV, MOD, false, PAC>(P, io, a_now, adtype, false, e, active, lane, warp_env0, nvalid, stage[wid],
-                                          use_zig ? zig_kiwi : nullptr,
-                                          io.obs + (int64_t)t * P.obs_elems, io.reward + (int64_t)t * n_envs,
-                                          io.done + (int64_t)t * n_envs, i, j, k, meta, tinfo, ep, ep_ret);
+            float* obs_t = io.obs + (int64_t)t * P.obs_elems;
+            float* rew_t = io.reward + (int64_t)t * n_envs;
+            uint8_t* done_t = io.done + (int64_t)t * n_envs;
+            if (FLAT) step_one_flat<MOD>(P, io, a_now, adtype, false, e, active, lane, warp_env0, nvalid, stage[wid], zig,
+                                         obs_t, rew_t, done_t, i, j, k, meta, tinfo, ep, ep_ret);
+            else step_one<NV, MOD, false, PAC>(P, io, a_now, adtype, false, e, active, lane, warp_env0, nvalid, stage[wid],
+                                               zig, obs_t, rew_t, done_t, i, j, k, meta, tinfo, ep, ep_ret);
         }
     }
     if (active) {

@@ -181,7 +181,7 @@ class PPO(PPOCore):
             _, reward, done = stepper.step_tensor(env_actions.contiguous())
             self.buf_rewards[t].copy_(reward)
             self._last_starts.copy_(done)
-            self._last_feat = features_tensor(self.env, out=self._last_feat)
+            self._last_feat = features_tensor(self.env, out=self._last_feat)     # (flat layout: a view, no kernel)
         last_values = self.policy.value(self._last_feat)
         gae(self.buf_rewards, self.buf_values, self.buf_starts, last_values.contiguous(), self._last_starts,
             self.gamma, self.gae_lambda, self.buf_adv, self.buf_ret)

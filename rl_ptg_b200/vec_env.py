@@ -121,9 +121,12 @@ class PtGVecEnv(_Base):
     def __init__(self, dict_input: dict, n_envs: int, train_or_eval: str = "train", render_mode: str = "None",
                  seed: int | None = None, device: str | torch.device = "cuda:0", noise: str = "numpy",
                  env_id_offset: int = 0, n_envs_global: int | None = None, obs_dtype=np.float32,
-                 info_limit: int = 4096):
+                 info_limit: int = 4096, obs_layout: str = "dict"):
         if noise not in _NOISE:
             raise ValueError(f"noise must be one of {sorted(_NOISE)}")
+        if obs_layout not in ("dict", "flat"):
+            raise ValueError('obs_layout must be "dict" (key-major blocks) or "flat" (one feature row per env)')
+        self.obs_layout = obs_layout
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("PtGVecEnv needs a CUDA device; there is no CPU fallback")
@@ -134,7 +137,8 @@ class PtGVecEnv(_Base):
         self.info_limit = info_limit
         self.n_envs_global = int(n_envs_global if n_envs_global is not None else n_envs)
         self.env_id_offset = int(env_id_offset)
-        self.cfg = _abi.config_from_kwargs(dict_input, train_or_eval, _NOISE[noise])
+        self.cfg = _abi.config_from_kwargs(dict_input, train_or_eval, _NOISE[noise],
+                                           obs_layout=_abi.OBS_FLAT if obs_layout == "flat" else _abi.OBS_KEY_MAJOR)
         tables, keep = _abi.tables_from_kwargs(dict_input, self.cfg.price_ahead)
         self.raw_modified = dict_input["raw_modified"]
         self.action_type = dict_input["action_type"]
@@ -154,6 +158,7 @@ class PtGVecEnv(_Base):
         del keep
         self._dev_index = dev_index
         self.obs_dim = self._L.ptg_obs_dim(self._h)
+        self.feature_dim = int(self._L.ptg_features_dim(self._h))
         self.obs_elems = int(self._L.ptg_obs_elems(self._h))
         keys = (_abi.PtgObsKey * 16)()
         nk = self._L.ptg_obs_layout(self._h, keys, 16)
@@ -190,7 +195,8 @@ class PtGVecEnv(_Base):
         self._t_start = time.time()
         self._ev_small = torch.cuda.Event()
         self._ev_scalars = torch.cuda.Event()
-        self._scalar_off = min(off for name, _, _, off in self.obs_keys if name == "METH_STATUS")
+        self._scalar_off = 0 if obs_layout == "flat" else min(off for name, _, _, off in self.obs_keys
+                                                               if name == "METH_STATUS")
         self.bytes_per_env_step = int(self._L.ptg_bytes_per_env_step(self._h, _TORCH_ACT[act_dtype]))
         if seed is not None:
             self.seed(seed)
@@ -216,24 +222,40 @@ class PtGVecEnv(_Base):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _obs_views(self, buf: torch.Tensor) -> dict:
-        """dict key -> [n_envs, dim] view of one obs buffer (torch tensor on any device)."""
+        """dict key -> [n_envs, dim] view of one obs buffer (torch tensor on any device).  Flat layout: strided
+        column views of the [n_envs, F] feature matrix (METH_STATUS = its six one-hot columns)."""
         n, out = self.num_envs, {}
+        if self.obs_layout == "flat":
+            rows = buf[:n * self.feature_dim].view(n, self.feature_dim)
+            for name, dim, _, col in self.obs_keys:
+                out[name] = rows[:, col:col + dim]
+            return out
         for name, dim, is_int, off in self.obs_keys:
             v = buf[off:off + n * dim]
             out[name] = v.view(torch.int32) if is_int else v.view(n, dim)
         return out
 
+    def features_view(self, buf: torch.Tensor | None = None) -> torch.Tensor:
+        """Flat layout only: the [n_envs, F] feature matrix of an obs buffer (default: the env's current one)."""
+        if self.obs_layout != "flat":
+            raise RuntimeError('features_view() needs obs_layout="flat" (use vec_normalize.features_tensor otherwise)')
+        buf = self._obs if buf is None else buf
+        return buf[:self.num_envs * self.feature_dim].view(self.num_envs, self.feature_dim)
+
     def _obs_numpy(self, buf_h: torch.Tensor, rows=None, status=None) -> dict:
         views = self._obs_views(buf_h)
         out = {}
         for name, dim, is_int, _ in self.obs_keys:
-            if is_int and status is not None:
+            if name == "METH_STATUS" and status is not None:
                 out[name] = status
                 continue
             a = views[name].numpy()
             if rows is not None:
                 a = a[rows]
-            out[name] = a.astype(np.int64) if is_int else a.astype(self.obs_dtype, copy=False)
+            if name == "METH_STATUS" and self.obs_layout == "flat":
+                out[name] = a.argmax(axis=1).astype(np.int64)        # one-hot columns -> Discrete(6) value
+            else:
+                out[name] = a.astype(np.int64) if is_int else a.astype(self.obs_dtype, copy=False)
         return out
 
     def _next_obs_host(self) -> torch.Tensor:
@@ -305,7 +327,8 @@ class PtGVecEnv(_Base):
         rewards = self._reward_h.numpy().copy()
         any_done = bool(dones.any())
         self._ev_scalars.synchronize()
-        status = self._obs_views(obs_h)["METH_STATUS"].numpy().astype(np.int64)
+        status = self._obs_views(obs_h)["METH_STATUS"].numpy()
+        status = status.argmax(axis=1).astype(np.int64) if self.obs_layout == "flat" else status.astype(np.int64)
         if any_done:
             self._term_obs_h.copy_(self._term_obs, non_blocking=True)
             self._ep_ret_h.copy_(self._ep_ret, non_blocking=True)

@@ -174,6 +174,12 @@ def feature_names(env: PtGVecEnv) -> list[str]:
 def features_tensor(env: PtGVecEnv, obs_buffer: torch.Tensor | None = None, out: torch.Tensor | None = None):
     """[n_envs, F] fp32 feature rows of the env's current observation (or of ``obs_buffer``, a flat obs buffer with
     the env's layout, e.g. ``rollout['obs'][t]``)."""
+    if env.obs_layout == "flat":                      # the step kernel already wrote the rows: zero-copy view
+        view = env.features_view(obs_buffer)
+        if out is None or out.data_ptr() == view.data_ptr():
+            return view
+        out.copy_(view)
+        return out
     L = _lib.load()
     F = feature_dim(env)
     src = env._obs if obs_buffer is None else obs_buffer

@@ -241,3 +241,65 @@ def test_vecnormalize_moment_records_combine_like_one_batch():
         assert np.allclose(torch.cat([out["a"], out["b"]]).cpu().numpy(), out["w"].cpu().numpy(), rtol=1e-6, atol=1e-9)
     for env in [whole] + halves:
         env.close()
+
+
+@pytest.mark.parametrize("design", ["mod", "raw"])
+@pytest.mark.parametrize("n_envs", [7, 256, 1000])
+def test_flat_layout_equals_dict_layout_plus_feature_kernel(design, n_envs):
+    """obs_layout="flat": the step kernel writes the CombinedExtractor rows itself.  Against the key-major env +
+    ptg_features on the same actions: identical rows, rewards, dones, states -- through resets, an episode end
+    (auto-reset + terminal observation), the roll-out kernel and the numpy API."""
+    import torch
+    from rl_ptg_b200.vec_env import PtGVecEnv
+    from rl_ptg_b200.vec_normalize import features_tensor
+    kw = dict(synthetic_kwargs(dict(scenario=3, operation="OP2", raw_modified=design)))
+    kw["eps_sim_steps"] = 40                              # short episodes: the auto-reset path runs several times
+    ed = PtGVecEnv(kw, n_envs, seed=5)
+    ef = PtGVecEnv(kw, n_envs, seed=5, obs_layout="flat")
+    F = ef.feature_dim
+    assert F == (40 if design == "mod" else 31) and ef.obs_elems >= n_envs * F
+    ed.reset_tensor(); ef.reset_tensor()
+    assert torch.equal(features_tensor(ed), ef.features_view())
+    assert features_tensor(ef).data_ptr() == ef._obs.data_ptr()          # zero-copy for the flat env
+    g = torch.Generator(device=ed.device); g.manual_seed(9)
+    for t in range(90):
+        a = torch.randint(0, 5, (n_envs,), generator=g, device=ed.device)
+        _, r1, d1 = ed.step_tensor(a)
+        _, r2, d2 = ef.step_tensor(a)
+        assert torch.equal(r1, r2) and torch.equal(d1, d2), f"step {t}"
+        assert torch.equal(features_tensor(ed), ef.features_view()), f"rows differ at step {t}"
+        if bool(d1.any()):
+            done = d1.bool()
+            assert torch.equal(features_tensor(ed, ed._term_obs)[done], ef.features_view(ef._term_obs)[done])
+    s1, s2 = ed.get_state(), ef.get_state()
+    for f in ("meth_state", "i", "j", "k", "hot_cold", "draws", "episode_count", "act_ep_h"):
+        assert np.array_equal(s1[f], s2[f]), f
+    # roll-out kernel
+    acts = torch.randint(0, 5, (12, n_envs), generator=g, device=ed.device)
+    ro_d, ro_f = ed.rollout_tensor(acts), ef.rollout_tensor(acts)
+    assert torch.equal(ro_d["reward"], ro_f["reward"]) and torch.equal(ro_d["done"], ro_f["done"])
+    for t in range(12):
+        assert torch.equal(features_tensor(ed, ro_d["obs"][t]), ef.features_view(ro_f["obs"][t])), f"rollout step {t}"
+    # masked reset + numpy API (dict of arrays, METH_STATUS back to Discrete values)
+    mask = (np.arange(n_envs) % 3 == 0).astype(np.uint8)
+    ed.reset_tensor(mask=mask); ef.reset_tensor(mask=mask)
+    assert torch.equal(features_tensor(ed), ef.features_view())
+    a = np.random.default_rng(0).integers(0, 5, n_envs)
+    o1, r1, d1, _ = ed.step(a)
+    o2, r2, d2, _ = ef.step(a)
+    assert set(o1) == set(o2)
+    for key in o1:
+        assert np.array_equal(np.asarray(o1[key]).reshape(n_envs, -1), np.asarray(o2[key]).reshape(n_envs, -1)), key
+    assert np.array_equal(r1, r2) and np.array_equal(d1, d2)
+    ed.close(); ef.close()
+
+
+def test_flat_layout_limits_fail_loudly():
+    from rl_ptg_b200._lib import PtgError
+    from rl_ptg_b200.vec_env import PtGVecEnv
+    with pytest.raises(PtgError, match="UNSUPPORTED"):
+        PtGVecEnv(synthetic_kwargs(dict(scenario=2, operation="OP2", price_ahead=6)), 8, obs_layout="flat")
+    with pytest.raises(PtgError, match="UNSUPPORTED"):
+        PtGVecEnv(synthetic_kwargs(dict(scenario=2, operation="OP2")), 8, train_or_eval="eval", obs_layout="flat")
+    with pytest.raises(ValueError):
+        PtGVecEnv(synthetic_kwargs(dict(scenario=2, operation="OP2")), 8, obs_layout="rows")

@@ -1,1 +1,2 @@
-python -m pytest tests/test_gpu_train_side.py -m gpu -x -q -k moment_records 2>&1 | tail -5
+python tools/microbench.py --steps 1000 --layout flat 2>&1 | grep -v "^$"
+python tools/microbench.py --steps 1000 --no-rollout 2>&1 | grep -v "^$"

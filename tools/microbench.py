@@ -17,9 +17,10 @@ ap.add_argument("--T", type=int, default=16)
 ap.add_argument("--policy", default="both", choices=["uniform", "sticky", "both"])
 ap.add_argument("--no-rollout", action="store_true")
 ap.add_argument("--noise", default="numpy", choices=["numpy", "off"])
+ap.add_argument("--layout", default="dict", choices=["dict", "flat"])
 args = ap.parse_args()
 kw = bench.make_kwargs()
-env = PtGVecEnv(kw, args.envs, seed=3654, noise=args.noise)
+env = PtGVecEnv(kw, args.envs, seed=3654, noise=args.noise, obs_layout=args.layout)
 env.reset_tensor()
 dev = env.device
 g = torch.Generator(device=dev); g.manual_seed(0)
@@ -41,7 +42,7 @@ for policy in (["uniform", "sticky"] if args.policy == "both" else [args.policy]
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / args.steps)
     ms = best
-    print(f"so={tag} noise={args.noise} {policy:8s} step: {ms*1e3:.1f} us/step  {args.envs/ms/1e6:.2f} G env-steps/s  "
+    print(f"so={tag} noise={args.noise} layout={args.layout} {policy:8s} step: {ms*1e3:.1f} us/step  {args.envs/ms/1e6:.2f} G env-steps/s  "
           f"{bpe*args.envs/ms/1e6:.0f} GB/s ({bpe} B/env-step)", flush=True)
     if args.no_rollout:
         continue
