@@ -46,6 +46,16 @@ CASES = {
                      dict(n_envs=2, steps=6000, actions="load2")),
     "bs2_op2_s50": (dict(scenario=2, operation="OP2", sim_step=100),
                     dict(n_envs=2, steps=6000, actions="load2")),
+    # narrower / wider hour rows than the default 13 (kernel instantiations NV = 3 and NV = 5), raw and mod
+    "bs3_op1_raw_pa6": (dict(scenario=3, operation="OP1", raw_modified="raw", price_ahead=6),
+                        dict(n_envs=2, steps=1500, actions="uniform")),
+    "bs1_op2_mod_pa16": (dict(scenario=1, operation="OP2", price_ahead=16),
+                         dict(n_envs=2, steps=1500, actions="load")),
+    # validation split in eval mode (EvalCallback env, src/rl_utils.py:456-469), continuous + raw + penalty
+    "bs2_op1_val_eval": (dict(scenario=2, operation="OP1"),
+                         dict(n_envs=2, steps=1200, actions="uniform", split="val", mode="eval", seed=605)),
+    "bs3_op2_raw_continuous_penalty": (dict(scenario=3, operation="OP2", raw_modified="raw", state_change_penalty=0.25),
+                                       dict(n_envs=2, steps=1500, actions="continuous", action_type="continuous")),
 }
 
 

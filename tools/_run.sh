@@ -1,2 +1,1 @@
-python tools/microbench.py --steps 1000 --no-rollout 2>&1 | grep -v "^$"
-PTG_B200_SO=$PWD/variants/nola.so python tools/microbench.py --steps 1000 --no-rollout 2>&1 | grep -v "^$"
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4
