@@ -157,6 +157,7 @@ class PPO(PPOCore):
         self.vn = VecNormalizeReward(env, gamma=0.99) if normalize_reward else None   # SB3 VecNormalize default gamma
         self._last_feat = None
         self._last_starts = torch.ones(self.n_envs, dtype=torch.uint8, device=self.device)
+        self._raw_reward_sum = torch.zeros((), dtype=torch.float64, device=self.device)
 
     # ------------------------------------------------------------------------------------------------------
     def _reset(self):
@@ -179,6 +180,7 @@ class PPO(PPOCore):
             self.buf_starts[t].copy_(self._last_starts)
             env_actions = actions.clamp(-1.0, 1.0).to(torch.float32) if self.continuous else actions
             _, reward, done = stepper.step_tensor(env_actions.contiguous())
+            self._raw_reward_sum += self.env._reward.sum(dtype=torch.float64)     # unnormalised env reward [ct]
             self.buf_rewards[t].copy_(reward)
             self._last_starts.copy_(done)
             self._last_feat = features_tensor(self.env, out=self._last_feat)     # (flat layout: a view, no kernel)
@@ -198,7 +200,9 @@ class PPO(PPOCore):
             ep = self.env.episode_stats(clear=True, reduce=False)
             stats.update(iteration=it, timesteps=self.num_timesteps, fps=self.num_timesteps / (time.perf_counter() - t0),
                          ep_rew_mean=ep["return_mean"], ep_len_mean=ep["length_mean"], episodes=ep["episodes"],
-                         mean_step_reward=float(self.buf_rewards.mean()))
+                         mean_step_reward=float(self.buf_rewards.mean()),
+                         env_reward_per_step=float(self._raw_reward_sum) / (self.n_steps * self.n_envs))
+            self._raw_reward_sum.zero_()
             self.logs.append(stats)
         return self
 
