@@ -210,6 +210,7 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     P.eps_sim_steps = c.eps_sim_steps; P.sim_step = c.sim_step;
     P.n_hours = (int32_t)tables->n_hours; P.n_days = (int32_t)tables->n_days;
     P.n_eps_ind = (int32_t)tables->n_eps_ind;
+    P.n_eps_loops = c.n_eps_loops;
     P.continuous = c.action_type; P.eval_mode = c.train_or_eval; P.noise_mode = c.noise_mode;
     P.schedule_mode = c.schedule_mode;
     P.penalty = c.reward_level * c.state_change_penalty;                       // :332

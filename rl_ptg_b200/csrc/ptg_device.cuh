@@ -168,6 +168,7 @@ struct DevParams {
     int32_t obs_dim;
     int32_t eps_sim_steps, sim_step;
     int32_t n_hours, n_days, n_vals, n_eps_ind;
+    int32_t n_eps_loops;       // SUBPROC schedule: start offsets are drawn from [0, n_eps_loops), :43-44
     int32_t raw;               // 1 = raw observation design
     int32_t flat;              // 1 = flat feature-row observation layout (PTG_OBS_FLAT)
     int32_t continuous, eval_mode, noise_mode, schedule_mode;

@@ -532,9 +532,11 @@ __global__ void k_construct(const __grid_constant__ DevParams P) {
     rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo; rr.draws = 0;
     P.rng[e] = rr;
     if (P.schedule_mode == PTG_SCHED_SUBPROC) {
-        // :43-44 draws ep_index from an UNSEEDED generator per worker process; here: a fixed stream per global id
+        // :43-44 draws ep_index = integers(0, n_eps_loops) from an UNSEEDED generator per worker process (not
+        // reproducible in the reference); here: a fixed stream per global env id, same range
         Pcg64 h = pcg64_from_seed(0x5eed0000ull + (uint64_t)gid);
-        P.ep_start[e] = (int32_t)(pcg64_next64(h) % (uint64_t)max(1, P.n_eps_ind > 0 ? P.n_eps_ind : 1));
+        const int range = max(1, min(P.n_eps_loops, P.n_eps_ind > 0 ? P.n_eps_ind : 1));
+        P.ep_start[e] = (int32_t)(pcg64_next64(h) % (uint64_t)range);
     } else {
         P.ep_start[e] = 0;
     }

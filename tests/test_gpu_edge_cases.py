@@ -256,3 +256,36 @@ def test_full_size_batch_equals_small_batches_of_the_same_global_ids():
         for f in INT_FIELDS:
             assert np.array_equal(s2[f], st[f][lo:lo + 2048]), f"{f} differs in window {lo}"
         assert np.array_equal(r2, rew[:, lo:lo + 2048])
+
+
+def test_subproc_schedule_mode():
+    """parallel == "Multiprocessing" (SubprocVecEnv, env/ptg_gym_env.py:43-44): every worker starts at its own random
+    position of eps_ind, drawn from [0, n_eps_loops), and walks it one entry per reset.  The reference draws that
+    position from an unseeded generator; here it is a fixed function of the global env id."""
+    kw = dict(synthetic_kwargs(dict(scenario=2, operation="OP2")))
+    kw["parallel"] = "Multiprocessing"
+    kw["eps_sim_steps"] = 30                                 # episodes of 25 steps: several resets in the test
+    n = 500
+    eps_ind, L = np.asarray(kw["eps_ind"]), len(kw["eps_ind"])
+    ep_h = lambda v: (v * kw["eps_len_d"] * 24).astype(np.int64)        # noqa: E731
+    env = make_env(kw, n, seed=3654)
+    seen = [env.get_state()["act_ep_h"].copy()]              # m = 0: constructor
+    env.reset()
+    seen.append(env.get_state()["act_ep_h"].copy())          # m = 1
+    a = np.zeros(n, dtype=np.int64)
+    for ep in range(3):
+        for t in range(25):
+            _, _, done, _ = env.step(a)
+        assert done.all()
+        seen.append(env.get_state()["act_ep_h"].copy())      # m = 2, 3, 4 (auto-reset)
+    seen = np.stack(seen)                                    # [5, n]
+    starts = np.full(n, -1)
+    for s in range(int(kw["n_eps_loops"])):
+        want = np.stack([ep_h(eps_ind[(s + m) % L]) for m in range(5)])          # [5]
+        hit = (seen == want[:, None]).all(axis=0) & (starts < 0)
+        starts[hit] = s
+    assert (starts >= 0).all(), "an env does not follow eps_ind from a start in [0, n_eps_loops)"
+    assert len(np.unique(starts)) > 20                       # the workers really start at different positions
+    env2 = make_env(kw, n, seed=999)                         # the schedule does not depend on the noise seed
+    assert np.array_equal(env2.get_state()["act_ep_h"], seen[0])
+    env.close(); env2.close()
