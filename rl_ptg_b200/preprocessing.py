@@ -100,9 +100,10 @@ def calculate_optimum(el_price_data, gas_price_data, eua_price_data, data_name: 
                                "Meth_CH4_flow", "Meth_H2O_flow", "Meth_el_heating"), start=4):
         stats[:, col] = np.asarray(ms[key], dtype=np.float64)[level]
     for col in range(8):
-        a = np.broadcast_to(np.asarray(parts[0][col], dtype=np.float64), (n,))
+        # reference quirk (rl_opt.py:113-124): the constituent columns are filled from the loop variables AFTER the
+        # partial/full loop, i.e. they always hold the FULL-load values, also where partial load was the better choice
         b = np.broadcast_to(np.asarray(parts[1][col], dtype=np.float64), (n,))
-        stats[:, 12 + col] = np.where(on, np.where(index == 1, b, a), 0.0)
+        stats[:, 12 + col] = np.where(on, b, 0.0)
     stats[:, 20] = rew
     stats[:, 21] = np.cumsum(np.where(on, rew, 0.0))
     stats[:, 23] = np.where(on, index, -1)

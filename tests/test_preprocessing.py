@@ -57,7 +57,33 @@ def test_config_validation():
 
 
 def test_synthetic_shapes():
+    from rl_ptg_b200 import _abi
     kw = synthetic_kwargs()
     assert kw["e_r_b"].shape == (3, 13, 36539) and kw["g_e"].shape == (2, 2, 1522)
-    assert kw["cooldown"].shape == (45001, 7) and sum(kw[k].shape[0] for k in ptg._abi.DATASET_NAMES) == 118760
+    assert kw["cooldown"].shape == (45001, 7) and sum(kw[k].shape[0] for k in _abi.DATASET_NAMES) == 118760
     assert set(np.unique(kw["e_r_b"][2])) <= {-1.0, 0.0, 1.0}
+
+
+def test_calculate_optimum_matches_reference_all_columns():
+    """All 24 columns of calculate_optimum (src/rl_opt.py:26-152) bit for bit against vectors recorded from the
+    unmodified reference (tests/golden/gen_golden_topt.py) -- including the reference's quirk that the revenue /
+    cost constituents always carry the full-load values."""
+    import json
+    import os
+    import numpy as np
+    import rl_ptg_b200 as ptg
+    from helpers import GOLDEN_DIR, REF_DATA
+    from rl_ptg_b200.config import STATS_NAMES
+    from rl_ptg_b200.preprocessing import calculate_optimum
+    with np.load(os.path.join(GOLDEN_DIR, "topt_reference.npz")) as z:
+        meta = json.loads(str(z["meta"]))
+        want = {m["name"]: z[m["name"]] for m in meta}
+    for m in meta:
+        E = ptg.EnvConfiguration(**m["overrides"])
+        price, _ = ptg.load_data_npz(REF_DATA, E)
+        s = m["split"]
+        d = calculate_optimum(price[f"el_price_{s}"], price[f"gas_price_{s}"], price[f"eua_price_{s}"], "Test_set",
+                              list(STATS_NAMES), E)
+        got = np.stack([d[k] for k in STATS_NAMES], axis=1)
+        assert list(STATS_NAMES) == m["stats_names"]
+        assert np.array_equal(got, want[m["name"]]), m["name"]
