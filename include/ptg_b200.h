@@ -250,6 +250,23 @@ int ptg_gae(int64_t n_envs, int32_t T, const float* rewards, const float* values
             const float* last_values, const uint8_t* last_dones, double gamma, double gae_lambda, float* advantages,
             float* returns, void* stream);
 
+/* calculate_optimum (src/rl_opt.py:26-152) on the device: the (n_hours, 24) statistics of the theoretical optimum
+ * T-OPT (columns = EnvConfiguration.stats_names, src/rl_config_env.py:44-49), whose columns 20 / 23 are the series
+ * behind the Pot_Reward / Part_Full observations.  The caller evaluates the level-dependent constants once per load
+ * level (off, partial, full; two evaluations of the PEM efficiency polynomial) in the reference's operation order;
+ * el / gas / eua and stats_out are device pointers, stats_out is row-major [n_hours][24] fp64. */
+typedef struct PtgOptLevel {
+    double q_gas;        /* (Q_ch4 + Q_h2_res)                       -> ch4_revenues = q_gas * gas */
+    double chp_rev, steam_rev, o2_rev;
+    double k_eua;        /* Meth_CO2_mass_flow / 1000 * 3600         -> eua_revenues = k_eua * eua * 100 */
+    double k_heat;       /* Meth_el_heating / 1000                   -> elec_costs_heating = k_heat * el */
+    double k_ely;        /* h2_volumeflow * H_u_H2 * 1000 / eta      -> elec_costs_electrolyzer = k_ely * el */
+    double water_cost;
+    double stat8[8];     /* Meth_State, Meth_Action, Meth_Hot_Cold, Meth_T_cat, H2, CH4, H2O, el_heating (cols 4..11) */
+} PtgOptLevel;
+int ptg_calculate_optimum(const double* el, int64_t n_hours, const double* gas, const double* eua, int64_t n_days,
+                          const PtgOptLevel* levels3, double* stats_out, void* stream);
+
 /* Sticky device-side error word (invalid action, market-table overrun, tape overrun).  Synchronises `stream`.
  * Returns PTG_OK or the first error seen since the last poll and clears it. */
 int ptg_poll_error(PtgHandle* h, void* stream);

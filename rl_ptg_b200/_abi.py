@@ -76,6 +76,11 @@ class PtgTables(C.Structure):
     ]
 
 
+class PtgOptLevel(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("q_gas", "chp_rev", "steam_rev", "o2_rev", "k_eua", "k_heat", "k_ely",
+                                          "water_cost")] + [("stat8", C.c_double * 8)]
+
+
 class PtgIO(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("terminal_obs", C.c_void_p),
                 ("info", C.c_void_p), ("episode_return", C.c_void_p), ("episode_length", C.c_void_p)]

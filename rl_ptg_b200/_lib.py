@@ -17,6 +17,7 @@ EXPORTS = (
     "ptg_obs_elems", "ptg_num_envs", "ptg_bytes_per_env_step", "ptg_kernel_launches", "ptg_host_standard_normal",
     "ptg_host_seed_state", "ptg_last_error",
     "ptg_abi_version", "ptg_vecnorm_moments", "ptg_vecnorm_apply", "ptg_features_dim", "ptg_features", "ptg_gae",
+    "ptg_calculate_optimum",
 )
 
 
@@ -62,6 +63,7 @@ def load(build_if_missing: bool = False):
     L.ptg_features_dim.argtypes = [vp]
     L.ptg_features.argtypes = [vp, vp, vp, vp]
     L.ptg_gae.argtypes = [i64, C.c_int32, vp, vp, vp, vp, vp, f64, f64, vp, vp, vp]
+    L.ptg_calculate_optimum.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp]
     L.ptg_obs_dim.argtypes = [vp]
     L.ptg_obs_layout.argtypes = [vp, C.POINTER(_abi.PtgObsKey), i32]
     L.ptg_obs_elems.argtypes = [vp]

@@ -653,6 +653,20 @@ extern "C" int ptg_gae(int64_t n_envs, int32_t T, const float* rewards, const fl
     return PTG_OK;
 }
 
+extern "C" int ptg_calculate_optimum(const double* el, int64_t n_hours, const double* gas, const double* eua,
+                                     int64_t n_days, const PtgOptLevel* levels3, double* stats_out, void* stream) {
+    if (!el || !gas || !eua || !levels3 || !stats_out) return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_hours < 1 || n_days < 1) return fail(PTG_ERR_INVALID_ARGUMENT, "empty price series");
+    if ((n_hours - 1) / 24 > n_days) return fail(PTG_ERR_INVALID_ARGUMENT, "gas/eua series shorter than the hourly series");
+    OptParams O;
+    for (int q = 0; q < 3; ++q) O.lv[q] = levels3[q];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    k_calculate_optimum<<<blocks_for(n_hours, 128), 128, 0, st>>>(el, n_hours, gas, eua, n_days, O, stats_out);
+    k_optimum_cumsum<<<1, 32, 0, st>>>(n_hours, stats_out);
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
 extern "C" void ptg_stats_combine(const PtgEpisodeStats* per_rank, int n_ranks, PtgEpisodeStats* out) {
     PtgEpisodeStats a{};
     a.min_return = INFINITY; a.max_return = -INFINITY;

@@ -267,3 +267,59 @@ __global__ void k_gae(int64_t n, int T, const float* __restrict__ rewards, const
         returns[q] = __fadd_rn(adv, v);
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// calculate_optimum (src/rl_opt.py:26-152): the per-hour theoretical optimum T-OPT whose columns 20 / 23 become the
+// Pot_Reward / Part_Full observations
+// ------------------------------------------------------------------------------------------------------------
+// Everything that depends only on the load level (partial / full) -- flows, the PEM efficiency polynomial, the
+// price-independent revenues -- is evaluated by the host in the reference's operation order (two levels); the kernel
+// does the per-hour part for both levels, picks the better one (ties -> partial load, like list.index(max(...))) and
+// writes the reference's (n_hours, 24) statistics row.  Column 21 (the running sum) is accumulated strictly
+// sequentially like the reference's `cum_rew += rew`, by one thread of a second launch.
+struct OptParams {
+    PtgOptLevel lv[3];      // off, partial load, full load
+};
+
+__global__ void k_calculate_optimum(const double* __restrict__ el, int64_t n_hours, const double* __restrict__ gas,
+                                    const double* __restrict__ eua, int64_t n_days,
+                                    const __grid_constant__ OptParams O, double* __restrict__ stats) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_hours) return;
+    int64_t t_day = t / 24;
+    if (t_day == n_days) t_day -= 1;                                   // rl_opt.py:52
+    const double e = el[t], g = gas[t_day], u = eua[t_day];
+    double rew_l[2], part[2][8];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        const PtgOptLevel& L = O.lv[l + 1];
+        const double ch4_rev = L.q_gas * g;
+        const double eua_rev = L.k_eua * u * 100;
+        const double heat_cost = L.k_heat * e;
+        const double ely_cost = L.k_ely * e;
+        const double elec_costs = heat_cost + ely_cost;
+        rew_l[l] = ch4_rev + L.chp_rev + L.steam_rev + eua_rev + L.o2_rev - elec_costs - L.water_cost;
+        part[l][0] = ch4_rev; part[l][1] = L.steam_rev; part[l][2] = L.o2_rev; part[l][3] = eua_rev;
+        part[l][4] = L.chp_rev; part[l][5] = -heat_cost; part[l][6] = -ely_cost; part[l][7] = -L.water_cost;
+    }
+    const int index = rew_l[1] > rew_l[0] ? 1 : 0;
+    const double rew = rew_l[index];
+    const bool on = rew > 0;
+    double* r = stats + t * 24;
+    r[0] = (double)t; r[1] = e; r[2] = g; r[3] = u;
+    const PtgOptLevel& S = O.lv[on ? index + 1 : 0];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r[4 + q] = S.stat8[q];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r[12 + q] = on ? part[1][q] : 0.0;     // reference quirk: always the full-load values
+    r[20] = rew;
+    r[21] = on ? rew : 0.0;                                            // summed up by k_optimum_cumsum
+    r[22] = 0.0;
+    r[23] = on ? (double)index : -1.0;
+}
+
+__global__ void k_optimum_cumsum(int64_t n_hours, double* __restrict__ stats) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double cum = 0.0;
+    for (int64_t t = 0; t < n_hours; ++t) { cum += stats[t * 24 + 21]; stats[t * 24 + 21] = cum; }
+}

@@ -207,3 +207,67 @@ class Preprocessing:
         else:
             kw.update(eps_ind=None, state_change_penalty=0.0)
         return kw
+
+
+def optimum_level_constants(EnvConfig: EnvConfiguration) -> list[dict]:
+    """The level-dependent part of ``calculate_optimum`` (rl_opt.py:56-100) for the levels [off, partial, full], in
+    the reference's operation order; the hour-dependent part is one multiplication per term (done per hour by the
+    host version above or by the CUDA kernel behind ``calculate_optimum_cuda``)."""
+    C = EnvConfig
+    ms = C.meth_stats_load
+    b_s3 = 1 if C.scenario == 3 else 0
+    out = []
+    for l in (0, 1, 2):
+        ch4_volumeflow = ms["Meth_CH4_flow"][l] * C.convert_mol_to_Nm3
+        h2_res_volumeflow = ms["Meth_H2_res_flow"][l] * C.convert_mol_to_Nm3
+        Q_ch4 = ch4_volumeflow * C.H_u_CH4 * 1000
+        Q_h2_res = h2_res_volumeflow * C.H_u_H2 * 1000
+        power_chp = Q_ch4 * C.eta_CHP * b_s3
+        Q_chp = Q_ch4 * (1 - C.eta_CHP) * b_s3
+        Q_steam = ms["Meth_H2O_flow"][l] * (C.dt_water * C.cp_water + C.h_H2O_evap) / 3600
+        h2_volumeflow = ms["Meth_H2_flow"][l] * C.convert_mol_to_Nm3
+        o2_volumeflow = 1 / 2 * h2_volumeflow * 3600
+        Meth_CO2_mass_flow = ms["Meth_CH4_flow"][l] * C.Molar_mass_CO2 / 1000
+        eta = electrolyzer_efficiency(h2_volumeflow / C.max_h2_volumeflow, C.min_load_electrolyzer)
+        water_elec = ms["Meth_H2_flow"][l] * C.Molar_mass_H2O / 1000 * 3600
+        out.append(dict(
+            q_gas=Q_ch4 + Q_h2_res, chp_rev=power_chp * C.eeg_el_price, steam_rev=(Q_steam + Q_chp) * C.heat_price,
+            o2_rev=o2_volumeflow * C.o2_price, k_eua=Meth_CO2_mass_flow / 1000 * 3600,
+            k_heat=ms["Meth_el_heating"][l] / 1000, k_ely=h2_volumeflow * C.H_u_H2 * 1000 / eta,
+            water_cost=(ms["Meth_H2O_flow"][l] + water_elec) / C.rho_water * C.water_price,
+            stat8=[float(ms[k][l]) for k in ("Meth_State", "Meth_Action", "Meth_Hot_Cold", "Meth_T_cat", "Meth_H2_flow",
+                                             "Meth_CH4_flow", "Meth_H2O_flow", "Meth_el_heating")]))
+    return out
+
+
+def calculate_optimum_cuda(el_price_data, gas_price_data, eua_price_data, data_name: str, stats_names,
+                           EnvConfig: EnvConfiguration, device="cuda:0", verbose: bool = False) -> dict:
+    """``calculate_optimum`` with the per-hour work on the GPU (``ptg_calculate_optimum``): same arguments, same
+    24-column dict, bit-identical values.  For sweeps over scenarios / operation points / price series."""
+    import ctypes as C_
+    import torch
+    from . import _abi, _lib
+    L = _lib.load()
+    dev = torch.device(device)
+    el = torch.as_tensor(np.ascontiguousarray(el_price_data, dtype=np.float64)).to(dev)
+    gas = torch.as_tensor(np.ascontiguousarray(gas_price_data, dtype=np.float64)).to(dev)
+    eua = torch.as_tensor(np.ascontiguousarray(eua_price_data, dtype=np.float64)).to(dev)
+    levels = (_abi.PtgOptLevel * 3)()
+    for q, lv in enumerate(optimum_level_constants(EnvConfig)):
+        for k, v in lv.items():
+            if k == "stat8":
+                for j, x in enumerate(v):
+                    levels[q].stat8[j] = x
+            else:
+                setattr(levels[q], k, float(v))
+    stats = torch.empty((el.numel(), 24), dtype=torch.float64, device=dev)
+    stream = C_.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(L.ptg_calculate_optimum(C_.c_void_p(el.data_ptr()), el.numel(), C_.c_void_p(gas.data_ptr()),
+                                       C_.c_void_p(eua.data_ptr()), gas.numel(), levels,
+                                       C_.c_void_p(stats.data_ptr()), stream))
+    host = stats.cpu().numpy()
+    stats_dict_opt = {name: host[:, m] for m, name in enumerate(stats_names)}
+    if verbose and data_name != "reward_Level":
+        print("    > ", data_name, ": Cumulative reward - theoretical optimum T-OPT = ",
+              round(stats_dict_opt["Meth_cum_reward_stats"][-EnvConfig.price_ahead], 2))
+    return stats_dict_opt

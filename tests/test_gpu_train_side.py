@@ -303,3 +303,33 @@ def test_flat_layout_limits_fail_loudly():
         PtGVecEnv(synthetic_kwargs(dict(scenario=2, operation="OP2")), 8, train_or_eval="eval", obs_layout="flat")
     with pytest.raises(ValueError):
         PtGVecEnv(synthetic_kwargs(dict(scenario=2, operation="OP2")), 8, obs_layout="rows")
+
+
+def test_calculate_optimum_on_device_is_bit_identical():
+    """calculate_optimum (src/rl_opt.py:26-152) with the per-hour work in a CUDA kernel --
+    all 24 columns bit-identical to the host version (which tests/test_preprocessing.py pins to vectors recorded from
+    the unmodified reference) and to those vectors directly; real data, three scenario / operation-point configs,
+    full training series (36 552 h)."""
+    import json
+    import os
+    import rl_ptg_b200 as ptg
+    from helpers import GOLDEN_DIR, REF_DATA
+    from rl_ptg_b200.config import STATS_NAMES
+    from rl_ptg_b200.preprocessing import calculate_optimum, calculate_optimum_cuda
+    with np.load(os.path.join(GOLDEN_DIR, "topt_reference.npz")) as z:
+        meta = json.loads(str(z["meta"]))
+        want = {m["name"]: z[m["name"]] for m in meta}
+    for m in meta:
+        E = ptg.EnvConfiguration(**m["overrides"])
+        price, _ = ptg.load_data_npz(REF_DATA, E)
+        for split in (m["split"], "train"):
+            args = (price[f"el_price_{split}"], price[f"gas_price_{split}"], price[f"eua_price_{split}"], "set",
+                    list(STATS_NAMES), E)
+            host = calculate_optimum(*args)
+            dev = calculate_optimum_cuda(*args)
+            for k in STATS_NAMES:
+                assert np.array_equal(host[k], dev[k]), (m["name"], split, k)
+        got = np.stack([calculate_optimum_cuda(price[f"el_price_{m['split']}"], price[f"gas_price_{m['split']}"],
+                                               price[f"eua_price_{m['split']}"], "set", list(STATS_NAMES), E)[k]
+                        for k in STATS_NAMES], axis=1)
+        assert np.array_equal(got, want[m["name"]])

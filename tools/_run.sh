@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_edge_cases.py -m gpu -x -q -k subproc 2>&1 | tail -12
+python -m pytest tests/test_gpu_train_side.py -m gpu -x -q -k calculate_optimum 2>&1 | tail -8
