@@ -137,6 +137,12 @@ typedef struct PtgIO {
                                 info (SB3 keeps the pre-reset info). Meth_Action is the action id 0..4. */
     double* episode_return;  /* [n_envs] Monitor-style sum of returned rewards of the episode that just ended */
     int32_t* episode_length; /* [n_envs] its length; both written only where done=1; NULL allowed */
+    uint32_t* windows_changed; /* one word or NULL (ptg_step, key-major layout): set to 1 when the step changed any
+                                  env's market-window blocks (Pot_Reward / Part_Full / Elec_Price / Gas_Price /
+                                  EUA_Price): they only move when an env's clock crosses an hour or its episode
+                                  ends, i.e. on one step in 3600 / sim_step.  Never cleared by the library: a
+                                  host mirror that zeroes it before the step may skip the transfer of those blocks
+                                  (3/4 of the observation bytes) when it still reads 0. */
 } PtgIO;
 
 /* One observation key of the obs buffer. */

@@ -708,6 +708,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
     // common case (no env of the warp ends its episode) can hand its window tiles to the TMA early
     const int done = active && (k == P.eps_sim_steps - 6);
     const bool any_done = __any_sync(0xffffffffu, done);
+    bool win_moved = false;
     if (active) {
         // (1) what the transition will need from memory
         const int action = decode_action_raw(P, action_raw, adtype, (meta >> 4) & 7);
@@ -721,6 +722,8 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         //     the NEW hour/day (:446-447) -> observation windows; sin/cos of the clock come from the clock table
         const unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
         int t_hour = ep.x + (int)(sec / 3600u), t_day = ep.y + (int)(sec / 86400u);
+        // the market-window blocks of the observation only move when the clock crosses an hour (or the episode ends)
+        win_moved = done || (sec / 3600u) != ((sec - (unsigned)P.sim_step) / 3600u);
         clamp_market_index(P, t_hour, t_day);
         load_hour_row<NV>(P, t_hour, hrow);
         day = load_day_row(P, t_day);
@@ -791,6 +794,8 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         st_stream(rew_out + e, reward);
         st_stream(done_out + e, (uint8_t)done);
     }
+    if (single && io.windows_changed != nullptr && __any_sync(0xffffffffu, win_moved) && lane == 0)
+        *io.windows_changed = 1u;                   // (same value from every warp: plain store, no atomic needed)
 }
 
 // One env step with the flat observation layout: the same transition / reward path as step_one, but the whole

@@ -182,6 +182,15 @@ class PtGVecEnv(_Base):
         # t + 2, which is what SB3's collect_rollouts needs (it stores the previous obs after the next step)
         self._obs_hh = [torch.zeros(self.obs_elems, dtype=torch.float32).pin_memory() for _ in range(2)]
         self._flip = 0
+        # The market-window blocks (3/4 of the observation bytes) only change when an env's clock crosses an hour or
+        # its episode ends: the step kernel raises `windows_changed` then, and the host mirror re-transfers those
+        # blocks only on such steps.  They live in whichever of the two host buffers received them last (_win_buf);
+        # a new version always goes to the OTHER buffer, so the dict handed out before stays intact.
+        self._win_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._win_flag_h = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._win_buf = 0
+        self._win_valid = False                  # host copy of the window blocks matches the device's
+        self.d2h_bytes = 0                       # bytes the numpy API copied device -> host so far
         self._term_obs_h = torch.zeros(self.obs_elems, dtype=torch.float32).pin_memory()
         self._reward_h = torch.zeros(n, dtype=torch.float32).pin_memory()
         self._done_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
@@ -216,6 +225,7 @@ class PtGVecEnv(_Base):
         io.info = info.data_ptr() if info is not None else None
         io.episode_return = ep_ret.data_ptr() if ep_ret is not None else None
         io.episode_length = ep_len.data_ptr() if ep_len is not None else None
+        io.windows_changed = None
         return io
 
     def _stream(self):
@@ -242,14 +252,16 @@ class PtGVecEnv(_Base):
         buf = self._obs if buf is None else buf
         return buf[:self.num_envs * self.feature_dim].view(self.num_envs, self.feature_dim)
 
-    def _obs_numpy(self, buf_h: torch.Tensor, rows=None, status=None) -> dict:
+    def _obs_numpy(self, buf_h: torch.Tensor, rows=None, status=None, win_buf_h: torch.Tensor | None = None) -> dict:
         views = self._obs_views(buf_h)
+        win_views = views if win_buf_h is None else self._obs_views(win_buf_h)
         out = {}
-        for name, dim, is_int, _ in self.obs_keys:
+        for name, dim, is_int, off in self.obs_keys:
             if name == "METH_STATUS" and status is not None:
                 out[name] = status
                 continue
-            a = views[name].numpy()
+            is_window = self.obs_layout != "flat" and off < self._scalar_off
+            a = (win_views if is_window else views)[name].numpy()
             if rows is not None:
                 a = a[rows]
             if name == "METH_STATUS" and self.obs_layout == "flat":
@@ -284,6 +296,8 @@ class PtGVecEnv(_Base):
         self.reset_tensor(_return_views=False)
         obs_h = self._next_obs_host()
         obs_h.copy_(self._obs, non_blocking=True)
+        self._win_buf, self._win_valid = self._flip, True
+        self.d2h_bytes += obs_h.numel() * 4
         self._info_h.copy_(self._info, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         self.poll_error()
@@ -303,8 +317,12 @@ class PtGVecEnv(_Base):
             a = a.astype(np.int64, copy=False).reshape(self.num_envs)
         self._act_h.numpy()[:] = a
         self._act_d.copy_(self._act_h, non_blocking=True)
+        if self.obs_layout != "flat":
+            self._win_flag.zero_()
+            self._io.windows_changed = self._win_flag.data_ptr()
         _lib.check(self._L.ptg_step(self._h, self._ptr(self._act_d), _TORCH_ACT[self._act_d.dtype],
                                     C.byref(self._io), self._stream()))
+        self._io.windows_changed = None
 
     def step_wait(self):
         obs_h = self._next_obs_host()
@@ -312,17 +330,26 @@ class PtGVecEnv(_Base):
         # small results first: the host can look at `dones` while the observation block is still in flight
         self._done_h.copy_(self._done, non_blocking=True)
         self._reward_h.copy_(self._reward, non_blocking=True)
+        self._win_flag_h.copy_(self._win_flag, non_blocking=True)
         self._ev_small.record(stream)
-        # the scalar blocks (METH_STATUS first) travel ahead of the two window blocks, so the int64 conversion of
+        # the scalar blocks (METH_STATUS first) travel ahead of the window blocks, so the int64 conversion of
         # METH_STATUS overlaps the rest of the transfer
         cut = self._scalar_off
         obs_h[cut:].copy_(self._obs[cut:], non_blocking=True)
         self._ev_scalars.record(stream)
-        obs_h[:cut].copy_(self._obs[:cut], non_blocking=True)
+        self.d2h_bytes += (obs_h.numel() - cut) * 4 + self.num_envs * 5 + 4
         eval_mode = bool(self.cfg.train_or_eval)
         if eval_mode:
             self._info_h.copy_(self._info, non_blocking=True)
+            self.d2h_bytes += self._info_h.numel() * 8
         self._ev_small.synchronize()
+        # window blocks: only when the step moved them (or the host copy is not known to be current)
+        if cut > 0 and (not self._win_valid or int(self._win_flag_h[0]) != 0):
+            # a new version goes to the buffer that does not hold the version handed out last
+            self._win_buf = (self._win_buf ^ 1) if self._win_valid else self._flip
+            self._obs_hh[self._win_buf][:cut].copy_(self._obs[:cut], non_blocking=True)
+            self._win_valid = True
+            self.d2h_bytes += cut * 4
         dones = self._done_h.numpy().view(np.bool_).copy()
         rewards = self._reward_h.numpy().copy()
         any_done = bool(dones.any())
@@ -361,7 +388,7 @@ class PtGVecEnv(_Base):
             infos = LazyInfos(self.num_envs, None, make if (eval_mode or any_done) else None)
         else:
             infos = [make(e) for e in range(self.num_envs)]
-        return self._obs_numpy(obs_h, status=status), rewards, dones, infos
+        return self._obs_numpy(obs_h, status=status, win_buf_h=self._obs_hh[self._win_buf]), rewards, dones, infos
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None:
@@ -446,6 +473,7 @@ class PtGVecEnv(_Base):
             mask_p = mask.ctypes.data
         io = self._make_io(self._obs, None, None, None, self._info)
         _lib.check(self._L.ptg_reset(self._h, seeds_p, mask_p, C.byref(io), self._stream()))
+        self._win_valid = False
         self._reset_seeds()
         return self._obs_dict if _return_views else None
 
@@ -457,6 +485,7 @@ class PtGVecEnv(_Base):
         if a.device != self.device or a.numel() != self.num_envs or not a.is_contiguous():
             raise ValueError("actions must be a contiguous CUDA tensor with n_envs elements on the env's device")
         _lib.check(self._L.ptg_step(self._h, self._ptr(a), _TORCH_ACT[a.dtype], C.byref(self._io), self._stream()))
+        self._win_valid = False                 # (the host mirror of the numpy API did not see this step)
         return self._obs_dict, self._reward, self._done
 
     def rollout_tensor(self, actions: torch.Tensor, out: dict | None = None):
@@ -474,6 +503,7 @@ class PtGVecEnv(_Base):
         io = self._make_io(out["obs"], out["reward"], out["done"])
         _lib.check(self._L.ptg_step_many(self._h, self._ptr(actions), _TORCH_ACT[actions.dtype], T, C.byref(io),
                                          self._stream()))
+        self._win_valid = False
         return out
 
     def capture_steps(self, action_buffers: Sequence[torch.Tensor]) -> "torch.cuda.CUDAGraph":
@@ -527,6 +557,7 @@ class PtGVecEnv(_Base):
             assert keep[name].shape == (self.num_envs,)
             setattr(s, name, keep[name].ctypes.data)
         _lib.check(self._L.ptg_set_state(self._h, C.byref(s)))
+        self._win_valid = False
 
     def kernel_launches(self) -> int:
         v = C.c_int64()

@@ -289,3 +289,42 @@ def test_subproc_schedule_mode():
     env2 = make_env(kw, n, seed=999)                         # the schedule does not depend on the noise seed
     assert np.array_equal(env2.get_state()["act_ep_h"], seen[0])
     env.close(); env2.close()
+
+
+def test_numpy_api_skips_unchanged_window_blocks_without_changing_results():
+    """The host mirror re-reads the market-window blocks only on steps that move them.  Against a second env whose
+    window cache is invalidated every step (every block travels): identical observations at every step, including
+    hour crossings, an episode end, and the obs dict of the PREVIOUS step staying intact (SB3 stores it after the
+    next step)."""
+    kw = dict(synthetic_kwargs(dict(scenario=2, operation="OP2")))
+    kw["eps_sim_steps"] = 45
+    n = 300
+    e1, e2 = make_env(kw, n, seed=8), make_env(kw, n, seed=8)
+    o1, o2 = e1.reset(), e2.reset()
+    rng = np.random.default_rng(6)
+    prev, prev_copy, skipped = None, None, 0
+    for t in range(100):
+        a = rng.integers(0, 5, size=n)
+        before = e1.d2h_bytes
+        o1, r1, d1, _ = e1.step(a)
+        skipped += (e1.d2h_bytes - before) < e1.obs_elems * 4
+        e2._win_valid = False                                  # force the full transfer
+        o2, r2, d2, _ = e2.step(a)
+        for k in o1:
+            assert np.array_equal(o1[k], o2[k]), f"{k} differs at step {t}"
+        assert np.array_equal(r1, r2) and np.array_equal(d1, d2)
+        if prev is not None:
+            for k in prev:
+                assert np.array_equal(prev[k], prev_copy[k]), f"previous obs[{k}] was overwritten at step {t}"
+        prev, prev_copy = o1, {k: v.copy() for k, v in o1.items()}
+    assert 70 <= skipped <= 90                                 # 5 of 6 steps (sim_step 600 s), minus episode ends
+    # mixing in the device API invalidates the host cache
+    import torch
+    e1.step_tensor(torch.zeros(n, dtype=torch.int64, device=e1.device))
+    e2.step_tensor(torch.zeros(n, dtype=torch.int64, device=e2.device))
+    o1, _, _, _ = e1.step(np.ones(n, dtype=np.int64))
+    e2._win_valid = False
+    o2, _, _, _ = e2.step(np.ones(n, dtype=np.int64))
+    for k in o1:
+        assert np.array_equal(o1[k], o2[k])
+    e1.close(); e2.close()

@@ -1,5 +1,3 @@
-python tools/sanitizer_smoke.py > gpurun_out/san_plain.log 2>&1 || { tail -5 gpurun_out/san_plain.log; exit 1; }
-for tool in memcheck racecheck; do
-  timeout 600 compute-sanitizer --tool $tool --error-exitcode 7 python tools/sanitizer_smoke.py > gpurun_out/san_$tool.log 2>&1; echo "$tool exit $?"
-  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitizer smoke done|=========   " gpurun_out/san_$tool.log | tail -5
-done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python tools/e2e_breakdown.py 2>&1 | grep "step()"
+python bench.py --steps 500 --no-cpu-baseline --no-rollout 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e'])"
