@@ -11,7 +11,9 @@
 #include "../../include/ptg_b200.h"
 #include "ptg_rng.cuh"
 
+#ifndef PTG_BLOCK
 #define PTG_BLOCK 256            // threads per CTA of the step kernels
+#endif
 #define PTG_N_ARGMIN 6           // argmin targets: cooldown, standby_up, standby_down, startup_cold, startup_hot, op1
 
 // --- step table entry: 64 B, 64 B aligned (exactly two 32 B sectors per gather) ---------------------------

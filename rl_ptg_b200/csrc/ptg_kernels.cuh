@@ -892,7 +892,7 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     static_assert(!FLAT || (NV == 4 && PAC == 13 && !EVAL), "the flat layout is built for price_ahead == 13");
     __shared__ __align__(128) float stage[PTG_BLOCK / 32][FLAT ? 32 * PTG_FLAT_F(MOD) : 2 * PTG_STAGE_FLOATS(NV)];
     __shared__ __align__(16) uint64_t zig_kiwi[2 * 256];   // {ki, wi} of numpy's ziggurat: 4 KB, one LDS.128 per draw
-    static_assert(PTG_BLOCK == 256, "one ziggurat layer per thread");
+    static_assert(256 % PTG_BLOCK == 0, "the CTA stages the 256 ziggurat layers in 256 / PTG_BLOCK rounds");
     const int n_envs = (int)P.n_envs;                   // < 2^26 (checked by ptg_create): 32-bit index arithmetic
     const int e = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -904,8 +904,11 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     asm volatile("griddepcontrol.launch_dependents;");
 #endif
     if (use_zig) {
-        zig_kiwi[2 * threadIdx.x] = __ldg(P.zig.ki + threadIdx.x);
-        zig_kiwi[2 * threadIdx.x + 1] = (uint64_t)__double_as_longlong(__ldg(P.zig.wi + threadIdx.x));
+#pragma unroll
+        for (int q = threadIdx.x; q < 256; q += PTG_BLOCK) {
+            zig_kiwi[2 * q] = __ldg(P.zig.ki + q);
+            zig_kiwi[2 * q + 1] = (uint64_t)__double_as_longlong(__ldg(P.zig.wi + q));
+        }
     }
 #if PTG_PDL
     // ... and nothing the previous kernel may still be writing (env state, actions) is touched before it completed

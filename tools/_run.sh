@@ -1,3 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/e2e_breakdown.py 2>&1 | grep "step()"
-python bench.py --steps 500 --no-cpu-baseline --no-rollout 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e'])"
+python bench.py > gpurun_out/bench_r01_e.json 2> gpurun_out/bench_err.log; cat gpurun_out/bench_r01_e.json | cut -c1-300; tail -2 gpurun_out/bench_err.log
