@@ -192,8 +192,9 @@ class PtGVecEnv(_Base):
         self._win_valid = False                  # host copy of the window blocks matches the device's
         self.d2h_bytes = 0                       # bytes the numpy API copied device -> host so far
         self._term_obs_h = torch.zeros(self.obs_elems, dtype=torch.float32).pin_memory()
-        self._reward_h = torch.zeros(n, dtype=torch.float32).pin_memory()
-        self._done_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        # rewards / dones: two pinned mirrors used alternately like the observation buffers, handed out as views
+        self._reward_hh = [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._done_hh = [torch.zeros(n, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self._info_h = torch.zeros((_abi.PTG_N_INFO, n), dtype=torch.float64).pin_memory()
         self._ep_ret_h = torch.zeros(n, dtype=torch.float64).pin_memory()
         self._ep_len_h = torch.zeros(n, dtype=torch.int32).pin_memory()
@@ -328,8 +329,9 @@ class PtGVecEnv(_Base):
         obs_h = self._next_obs_host()
         stream = torch.cuda.current_stream(self.device)
         # small results first: the host can look at `dones` while the observation block is still in flight
-        self._done_h.copy_(self._done, non_blocking=True)
-        self._reward_h.copy_(self._reward, non_blocking=True)
+        done_h, reward_h = self._done_hh[self._flip], self._reward_hh[self._flip]
+        done_h.copy_(self._done, non_blocking=True)
+        reward_h.copy_(self._reward, non_blocking=True)
         self._win_flag_h.copy_(self._win_flag, non_blocking=True)
         self._ev_small.record(stream)
         # the scalar blocks (METH_STATUS first) travel ahead of the window blocks, so the int64 conversion of
@@ -350,8 +352,8 @@ class PtGVecEnv(_Base):
             self._obs_hh[self._win_buf][:cut].copy_(self._obs[:cut], non_blocking=True)
             self._win_valid = True
             self.d2h_bytes += cut * 4
-        dones = self._done_h.numpy().view(np.bool_).copy()
-        rewards = self._reward_h.numpy().copy()
+        dones = done_h.numpy().view(np.bool_)          # views: valid until the step after next, like the obs dict
+        rewards = reward_h.numpy()
         any_done = bool(dones.any())
         self._ev_scalars.synchronize()
         status = self._obs_views(obs_h)["METH_STATUS"].numpy()
@@ -375,10 +377,11 @@ class PtGVecEnv(_Base):
                 term = {k: v.copy() for k, v in term.items()}
                 ret, length = ret.copy(), length.copy()
         t_now = round(time.time() - self._t_start, 6)
+        done_snap = dones.copy() if any_done else None      # (the returned `dones` is a view of a reused mirror)
 
         def make(e):
             d = self._info_dict(info_a[:, e]) if info_a is not None else {}
-            if any_done and dones[e]:
+            if any_done and done_snap[e]:
                 d["episode"] = {"r": round(float(ret[e]), 6), "l": int(length[e]), "t": t_now}   # Monitor
                 d["TimeLimit.truncated"] = False                     # the env only ever terminates (:478-481)
                 d["terminal_observation"] = {k: v[e] for k, v in term.items()}

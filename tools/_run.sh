@@ -1,1 +1,3 @@
-python bench.py > gpurun_out/bench_r01_e.json 2> gpurun_out/bench_err.log; cat gpurun_out/bench_r01_e.json | cut -c1-300; tail -2 gpurun_out/bench_err.log
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python __graft_entry__.py smoke 2>&1 | tail -1
+python tools/e2e_breakdown.py 2>&1 | grep "step()"

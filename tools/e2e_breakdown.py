@@ -22,7 +22,6 @@ a = env._act_h.numpy()
 print("host copy actions 8 MB  %.2f ms" % T(lambda: a.__setitem__(slice(None), acts[1])))
 print("H2D actions             %.2f ms" % T(lambda: env._act_d.copy_(env._act_h, non_blocking=True)))
 print("_obs_numpy              %.2f ms" % T(lambda: env._obs_numpy(h)))
-print("reward copy             %.2f ms" % T(lambda: env._reward_h.numpy().copy()))
 print("poll_error              %.2f ms" % T(lambda: env.poll_error()))
 big = torch.empty(1 << 28, dtype=torch.uint8, device=env.device); hb = torch.empty(1 << 28, dtype=torch.uint8).pin_memory()
 ms = T(lambda: hb.copy_(big, non_blocking=True), 5)
