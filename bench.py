@@ -281,7 +281,9 @@ def run_gpu(args):
             rate, dt = cpu_oracle_rate(kw, n_cpu, args.cpu_lock_steps, cores)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"CPU oracle (C restatement of PTGEnv, pthreads), {n_cpu} envs x {args.cpu_lock_steps} "
-                             f"lock-steps = {dt:.1f} s"}
+                             f"lock-steps = {dt:.1f} s",
+                   "note": "a compiled port: the Python reference itself steps ~1.0e4 env-steps/s per core and "
+                           "~9.6e3 in total under an 8-process SubprocVecEnv-style harness (BASELINE.md section 2)"}
         line = {
             "metric": METRIC, "value": n_global * K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
