@@ -256,7 +256,8 @@ __global__ void k_gae(int64_t n, int T, const float* __restrict__ rewards, const
         advantages[q] = adv;
         returns[q] = __fadd_rn(adv, v);
     }
-    for (int t = T - 2; t >= 0; --t) {
+#pragma unroll 8
+    for (int t = T - 2; t >= 0; --t) {      // (unrolled: the loads of 8 steps are in flight together)
         const int64_t q = (int64_t)t * n + e, qn = q + n;
         const float nnt = __fsub_rn(1.0f, (float)episode_starts[qn]);
         const float v = values[q];
