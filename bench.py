@@ -36,8 +36,9 @@ if ROOT not in sys.path:
 
 ENVS_PER_GPU = 1 << 20
 # Algorithmic HBM bytes of one transition-noise draw (numpy-exact PCG64 state lives in HBM per env): PCG64 state
-# 16 B read + 16 B written, increment 16 B read, draw counter 8 B read + 8 B written.
-RNG_BYTES_PER_DRAW = 64
+# 16 B read + 16 B written, increment 16 B read; the draw counter rides in spare bits of the per-step state word
+# (DESIGN.md section 3).
+RNG_BYTES_PER_DRAW = 48
 WORKLOAD = "BS2/OP2 mod, discrete int64 actions, train episodes, synthetic data of repo shapes"
 METRIC, UNIT = "env-steps/sec", "env-steps/s"
 

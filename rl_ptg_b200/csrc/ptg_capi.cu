@@ -287,7 +287,7 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     }
     std::sort(tvals.begin(), tvals.end());
     tvals.erase(std::unique(tvals.begin(), tvals.end()), tvals.end());
-    if (tvals.size() >= (1u << 28)) { ptg_destroy(h); return fail(PTG_ERR_UNSUPPORTED, "too many distinct temperatures"); }
+    if (tvals.size() >= (1u << PTG_TI_ID_BITS)) { ptg_destroy(h); return fail(PTG_ERR_UNSUPPORTED, "too many distinct temperatures"); }
     B.S = P.S; B.n_entries = ent; B.n_vals = (int32_t)tvals.size(); P.n_vals = B.n_vals;
     PTG_TRY(h->upload(&B.vals, tvals.data(), tvals.size()));
     h->d_vals = const_cast<double*>(B.vals);

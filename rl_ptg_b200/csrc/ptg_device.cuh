@@ -39,6 +39,13 @@ struct __align__(16) StepMeans {
 #define PTG_TF_COLD 1       // T <= t_cat_startup_cold   (:339)
 #define PTG_TF_HOT 2        // T >= t_cat_startup_hot    (:341)
 #define PTG_TF_SBUP 4       // T <= t_cat_standby        (:579)
+// per-env `tinfo` word: [0,3) flags | [3,20) T value id | [20,32) noise draws since the last fold into RngRec
+#define PTG_TI_ID_BITS 17
+#define PTG_TI_DRAW_SHIFT 20
+#define PTG_TI_DRAW_MAX 0xfffu
+#define PTG_TI_LOW_MASK 0xfffffu
+PTG_HD int ti_id(int32_t t) { return (int)(((uint32_t)t >> 3) & ((1u << PTG_TI_ID_BITS) - 1u)); }
+PTG_HD uint32_t ti_draws(int32_t t) { return (uint32_t)t >> PTG_TI_DRAW_SHIFT; }
 
 // --- day row: 32 B ------------------------------------------------------------------------------------------
 struct __align__(16) DayRow {
@@ -101,13 +108,14 @@ struct RewardConsts {
     int32_t b_s3, _pad;
 };
 
-// --- per-env noise generator: ONE 64 B line; sector 0 is read-modify-written by a draw, sector 1 is constant ---
+// --- per-env noise generator: sector 0 of a 64 B line holds everything a draw needs (one 256-bit load, one 128-bit
+//     store); the 64-bit draw counter lives in the cold sector 1 and is only touched when the 12-bit per-env counter
+//     that rides in the spare bits of `tinfo` (already streamed every step) overflows ---
 struct __align__(16) RngRec {
     uint64_t s_hi, s_lo;   // PCG64 state
-    int64_t draws;         // normal draws consumed so far (tape position in tape mode)
-    uint64_t _pad0;
-    uint64_t i_hi, i_lo;   // PCG64 increment
-    uint64_t _pad1, _pad2;
+    uint64_t i_hi, i_lo;   // PCG64 increment (constant per seed)
+    int64_t draws_total;   // draws folded in from the tinfo counter so far (tape position = draws_total + counter)
+    uint64_t _pad0, _pad1, _pad2;
 };
 static_assert(sizeof(RngRec) == 64, "RngRec layout");
 
@@ -210,7 +218,7 @@ struct DevParams {
     int64_t obs_elems;             // total fp32 elements of one obs buffer
     // per-env state (device, SoA)
     int4* core;                    // i, j, k, meta
-    int32_t* tinfo;                // (T value id << 3) | flags
+    int32_t* tinfo;                // flags | T value id << 3 | 12-bit draw counter << 20 (ti_id / ti_draws)
     int2* ep;                      // act_ep_h, act_ep_d
     double* ep_ret;                // Monitor-style running return (sum of returned rewards)
     int32_t* ep_count;             // constructor/resets consumed (m)
@@ -247,38 +255,40 @@ struct RewardParts {
 
 #if defined(__CUDACC__)
 
-// The RNG record of a drawing lane: both 32 B sectors are requested back to back (sector 0 = state + draw counter,
-// read-modify-written; sector 1 = the constant increment, non-coherent path), then consumed by draw_noise.
+// The RNG record of a drawing lane: state and increment share one 32 B sector -> ONE 256-bit request per draw.
 struct RngLoad {
-    U256 lo;            // {s_hi, s_lo, draws, pad}
-    ulonglong2 inc;     // {i_hi, i_lo}
+    U256 lo;            // {s_hi, s_lo, i_hi, i_lo}
 };
 __device__ __forceinline__ RngLoad request_rng(const DevParams& P, int64_t e) {
-    const RngRec* rec = P.rng + e;
     RngLoad r;
-    r.inc = make_ulonglong2(0, 0);
-    if (P.noise_mode == PTG_NOISE_NUMPY)
-        asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(r.inc.x), "=l"(r.inc.y) : "l"(reinterpret_cast<const char*>(rec) + 32));
-    r.lo = ld256(rec);
+    r.lo = ld256(P.rng + e);
     return r;
 }
 
 // One draw of np_random.normal(0, noise, size=1)[0].  (Measured: inlining beats an out-of-line call here -- the
 // call's register save/restore costs more than the 128-bit PCG64 arithmetic adds to the live set.)
-__device__ __forceinline__ double draw_noise(const DevParams& P, int64_t e, const uint64_t* zig_kiwi, const RngLoad& r) {
+// draws_ep: the env's 12-bit draw counter (from tinfo), incremented here and folded into the record when it is full.
+__device__ __forceinline__ double draw_noise(const DevParams& P, int64_t e, const uint64_t* zig_kiwi, const RngLoad& r,
+                                             uint32_t& draws_ep) {
     RngRec* rec = P.rng + e;
-    const int64_t d = (int64_t)r.lo.c;
-    rec->draws = d + 1;
+    double out;
     if (P.noise_mode == PTG_NOISE_TAPE) {
-        if (d >= P.tape_len) { atomicOr(P.err, PTG_EBIT_TAPE); return 0.0; }
-        return P.tape[e * P.tape_len + d];
+        const int64_t d = rec->draws_total + (int64_t)draws_ep;
+        if (d >= P.tape_len) { atomicOr(P.err, PTG_EBIT_TAPE); out = 0.0; }
+        else out = P.tape[e * P.tape_len + d];
+    } else {
+        Pcg64 g = {r.lo.a, r.lo.b, r.lo.c, r.lo.d};
+        ZigTables zt = P.zig;
+        zt.kiwi = zig_kiwi;         // the CTA's shared-memory copy of the hot {ki, wi} pairs
+        const double z = pcg64_standard_normal(g, zt);
+        reinterpret_cast<ulonglong2*>(rec)[0] = make_ulonglong2(g.s_hi, g.s_lo);
+        out = 0.0 + P.noise * z;    // random_normal: loc + scale * standard_normal
     }
-    Pcg64 g = {r.lo.a, r.lo.b, r.inc.x, r.inc.y};
-    ZigTables zt = P.zig;
-    zt.kiwi = zig_kiwi;             // the CTA's shared-memory copy of the hot {ki, wi} pairs
-    const double z = pcg64_standard_normal(g, zt);
-    reinterpret_cast<ulonglong2*>(rec)[0] = make_ulonglong2(g.s_hi, g.s_lo);
-    return 0.0 + P.noise * z;      // random_normal: loc + scale * standard_normal
+    if (++draws_ep == PTG_TI_DRAW_MAX) {            // rare: fold the small counter into the 64-bit one
+        rec->draws_total += (int64_t)PTG_TI_DRAW_MAX;
+        draws_ep = 0;
+    }
+    return out;
 }
 
 // i = int(max(argmin + noise, 0)), :584-585
@@ -391,7 +401,8 @@ __device__ __forceinline__ Plan plan_transition(int action, uint32_t& meta, int 
 }
 
 __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, const Plan& p, int& i, int& j,
-                                                uint32_t& meta, int lut_val, const uint64_t* zig_kiwi) {
+                                                uint32_t& meta, int lut_val, const uint64_t* zig_kiwi,
+                                                uint32_t& draws_ep) {
     const int S = P.S;
     int state = meta & 7, ds = p.ds, next_state, change = 0;
     if (p.kind == PTG_KIND_CONT) {
@@ -408,7 +419,7 @@ __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, c
         }
         meta = meta_set_tab(meta, state, ds);
         double nz = 0.0;
-        if (P.noise_mode != PTG_NOISE_OFF) nz = draw_noise(P, e, zig_kiwi, request_rng(P, e));
+        if (P.noise_mode != PTG_NOISE_OFF) nz = draw_noise(P, e, zig_kiwi, request_rng(P, e), draws_ep);
         i = jitter_index(lut_val, nz);
         j = 1;
     } else {                                                                     // _partial / _full

@@ -515,7 +515,7 @@ __device__ __forceinline__ void env_reset_state(const DevParams& P, int64_t e, i
     m.part_ds = PTG_DS_OP1_START_P; m.full_ds = PTG_DS_OP2_START_F;
     // current_action is NOT touched by reset() (only by __init__, :143)
     core = make_int4(P.reset_i, 0, 0, (int)meta_pack(m));
-    tinfo = P.reset_tinfo;
+    tinfo = (int32_t)((uint32_t)P.reset_tinfo | ((uint32_t)tinfo & ~PTG_TI_LOW_MASK));    // (in/out: draw counter kept)
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -529,7 +529,7 @@ __global__ void k_construct(const __grid_constant__ DevParams P) {
     // SeedSequence(global id) so that an unseeded run is still reproducible.
     Pcg64 g = pcg64_from_seed((uint64_t)gid);
     RngRec rr = {};
-    rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo; rr.draws = 0;
+    rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo; rr.draws_total = 0;
     P.rng[e] = rr;
     if (P.schedule_mode == PTG_SCHED_SUBPROC) {
         // :43-44 draws ep_index = integers(0, n_eps_loops) from an UNSEEDED generator per worker process (not
@@ -542,7 +542,7 @@ __global__ void k_construct(const __grid_constant__ DevParams P) {
     }
     Meta m;
     m.cur_action = PTG_COOLDOWN;     // :143
-    int4 core; int32_t tinfo; int2 ep;
+    int4 core; int32_t tinfo = 0; int2 ep;
     env_reset_state(P, e, 0, core, tinfo, ep, m);
     P.core[e] = core; P.tinfo[e] = tinfo; P.ep[e] = ep;
     P.ep_ret[e] = 0.0; P.ep_count[e] = 0;
@@ -570,15 +570,17 @@ __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ Dev
     int t_hour = 0, t_day = 0;
     Meta m = {};
     if (doit) {
-        if (seeds != nullptr && seeds[e] >= 0) {          // gymnasium Env.reset(seed=...)
+        int32_t tinfo = P.tinfo[e];                       // (its draw-counter bits survive a plain reset)
+        if (seeds != nullptr && seeds[e] >= 0) {          // gymnasium Env.reset(seed=...): a fresh generator
             Pcg64 g = pcg64_from_seed((uint64_t)seeds[e]);
             RngRec rr = {};
-            rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo; rr.draws = 0;
+            rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo; rr.draws_total = 0;
             P.rng[e] = rr;
+            tinfo = 0;
         }
         m = meta_unpack((uint32_t)P.core[e].w);
         const int32_t mc = P.ep_count[e] + 1;
-        int4 core; int32_t tinfo; int2 ep;
+        int4 core; int2 ep;
         env_reset_state(P, e, mc, core, tinfo, ep, m);
         P.core[e] = core; P.tinfo[e] = tinfo; P.ep[e] = ep; P.ep_count[e] = mc; P.ep_ret[e] = 0.0;
         if (P.has_penalty) P.nchg[e] = 0;
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ Dev
 // finished-episode accumulators and write the reset state (next entry of the episode schedule) to global memory.
 template <int NV, bool MOD, bool FLAT = false>
 __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io, int64_t e, bool record, int k,
-                                            double ep_ret, int cur_action, ObsKey key) {
+                                            double ep_ret, int cur_action, ObsKey key, uint32_t draws_ep) {
     if (record) {
         if (io.terminal_obs != nullptr) {
             if (FLAT) emit_flat_row<MOD>(P, io.terminal_obs, e, key);
@@ -628,7 +630,7 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
     P.ep_count[e] = mc;
     Meta m;
     m.cur_action = cur_action;
-    int4 core; int32_t tinfo; int2 ep;
+    int4 core; int32_t tinfo = (int32_t)(draws_ep << PTG_TI_DRAW_SHIFT); int2 ep;
     env_reset_state(P, e, mc, core, tinfo, ep, m);
     P.core[e] = core; P.tinfo[e] = tinfo; P.ep[e] = ep; P.ep_ret[e] = 0.0;
     if (P.has_penalty) P.nchg[e] = 0;
@@ -714,8 +716,9 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         const int action = decode_action_raw(P, action_raw, adtype, (meta >> 4) & 7);
         const int prev_state = meta & 7;
         const Plan plan = plan_transition(action, meta, tinfo & 7);
+        uint32_t draws_ep = ti_draws(tinfo);
         int lut_val = 0;
-        if (plan.col >= 0) lut_val = ldg32_nc_keep(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + plan.col);
+        if (plan.col >= 0) lut_val = ldg32_nc_keep(P.argmin_lut + ti_id(tinfo) * PTG_N_ARGMIN + plan.col);
         const bool draws = plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF;
         if (draws) prefetch_l1(P.rng + e);
         // (2) clock of step k+1 (:442-445, integer form of floor(clock_hours), floor(clock_days)) -> market rows of
@@ -734,7 +737,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         // thread's outstanding accesses, so it must not sit behind the RNG / step-table requests
         if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
         // (3) plant transition (requests the RNG record when it draws) -> step-table entry (2 x 32 B sectors)
-        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi);
+        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep);
         const int state_change = (prev_state != (int)(meta & 7));
         U256 qc, qn;      // qc = {c_gas, c_eua, c_el, c_0}, qn = {norm[6], tinfo, pad}
         gather_step_entry(P, ent, lane, nvalid, qc, qn);
@@ -748,7 +751,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         o.norm[0] = __uint_as_float((uint32_t)qn.a); o.norm[1] = __uint_as_float((uint32_t)(qn.a >> 32));
         o.norm[2] = __uint_as_float((uint32_t)qn.b); o.norm[3] = __uint_as_float((uint32_t)(qn.b >> 32));
         o.norm[4] = __uint_as_float((uint32_t)qn.c); o.norm[5] = __uint_as_float((uint32_t)(qn.c >> 32));
-        tinfo = (int32_t)(uint32_t)qn.d;
+        tinfo = (int32_t)(((uint32_t)qn.d & PTG_TI_LOW_MASK) | (draws_ep << PTG_TI_DRAW_SHIFT));
         o.status = meta & 7;
         o.sin_h = sc2.x; o.cos_h = sc2.y;
         uint32_t nchg = 0;
@@ -758,7 +761,8 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
                                                   ep_ret + (double)nchg * P.penalty});
         k += 1;
         if (done) {                                   // SB3 auto-reset (DummyVecEnv.step_wait), out of line
-            finish_episode<NV, MOD>(P, io, e, single, k, ep_ret, (meta >> 4) & 7, ObsKey{ent, t_hour, t_day, (int)(meta & 7), k});
+            finish_episode<NV, MOD>(P, io, e, single, k, ep_ret, (meta >> 4) & 7, ObsKey{ent, t_hour, t_day, (int)(meta & 7), k},
+                                    draws_ep);
             const int4 core = P.core[e];              // the reset state written by finish_episode
             tinfo = P.tinfo[e]; ep = P.ep[e];
             i = core.x; j = core.y; k = core.z; meta = (uint32_t)core.w; ep_ret = 0.0;
@@ -820,8 +824,9 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
         const int action = decode_action_raw(P, action_raw, adtype, (meta >> 4) & 7);
         const int prev_state = meta & 7;
         const Plan plan = plan_transition(action, meta, tinfo & 7);
+        uint32_t draws_ep = ti_draws(tinfo);
         int lut_val = 0;
-        if (plan.col >= 0) lut_val = ldg32_nc_keep(P.argmin_lut + (tinfo >> 3) * PTG_N_ARGMIN + plan.col);
+        if (plan.col >= 0) lut_val = ldg32_nc_keep(P.argmin_lut + ti_id(tinfo) * PTG_N_ARGMIN + plan.col);
         if (plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF) prefetch_l1(P.rng + e);
         const unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
         int t_hour = ep.x + (int)(sec / 3600u), t_day = ep.y + (int)(sec / 86400u);
@@ -831,7 +836,7 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
         const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + (k + 1)));
         stage_flat_early<MOD>(row, hrow, day, pf0, pr12);
         const double el = hour_row_el<4>(hrow);
-        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi);
+        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep);
         const int state_change = (prev_state != (int)(meta & 7));
         U256 qc, qn;
         gather_step_entry(P, ent, lane, nvalid, qc, qn);
@@ -844,14 +849,14 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
         o.norm[0] = __uint_as_float((uint32_t)qn.a); o.norm[1] = __uint_as_float((uint32_t)(qn.a >> 32));
         o.norm[2] = __uint_as_float((uint32_t)qn.b); o.norm[3] = __uint_as_float((uint32_t)(qn.b >> 32));
         o.norm[4] = __uint_as_float((uint32_t)qn.c); o.norm[5] = __uint_as_float((uint32_t)(qn.c >> 32));
-        tinfo = (int32_t)(uint32_t)qn.d;
+        tinfo = (int32_t)(((uint32_t)qn.d & PTG_TI_LOW_MASK) | (draws_ep << PTG_TI_DRAW_SHIFT));
         o.status = meta & 7;
         o.sin_h = sc2.x; o.cos_h = sc2.y;
         if (P.has_penalty) P.nchg[e] += (uint32_t)state_change;
         k += 1;
         if (done) {                                   // SB3 auto-reset: the returned row is the reset observation
             finish_episode<4, MOD, true>(P, io, e, single, k, ep_ret, (meta >> 4) & 7,
-                                         ObsKey{ent, t_hour, t_day, (int)(meta & 7), k});
+                                         ObsKey{ent, t_hour, t_day, (int)(meta & 7), k}, draws_ep);
             const int4 core = P.core[e];
             tinfo = P.tinfo[e]; ep = P.ep[e];
             i = core.x; j = core.y; k = core.z; meta = (uint32_t)core.w; ep_ret = 0.0;
@@ -1048,8 +1053,8 @@ __global__ void k_state_unpack(const __grid_constant__ DevParams P, StateDev s, 
     s.partial_ds[e] = m.part_ds; s.full_ds[e] = m.full_ds; s.current_action[e] = m.cur_action;
     const int2 ep = P.ep[e];
     s.act_ep_h[e] = ep.x; s.act_ep_d[e] = ep.y; s.episode_count[e] = P.ep_count[e];
-    s.draws[e] = P.rng[e].draws;
-    s.t_cat[e] = vals[P.tinfo[e] >> 3];
+    s.draws[e] = P.rng[e].draws_total + (int64_t)ti_draws(P.tinfo[e]);
+    s.t_cat[e] = vals[ti_id(P.tinfo[e])];
     s.cum_reward[e] = P.ep_ret[e];
 }
 
@@ -1063,7 +1068,7 @@ __global__ void k_state_pack(const __grid_constant__ DevParams P, StateDev s, co
     P.core[e] = make_int4(s.i[e], s.j[e], s.k[e], (int)meta_pack(m));
     P.ep[e] = make_int2(s.act_ep_h[e], s.act_ep_d[e]);
     P.ep_count[e] = s.episode_count[e];
-    P.rng[e].draws = s.draws[e];
+    P.rng[e].draws_total = s.draws[e];            // (the 12-bit counter in tinfo restarts at 0 below)
     P.tinfo[e] = tinfo_of(B, s.t_cat[e]);        // t_cat must be a temperature present in the tables (or 16)
     P.ep_ret[e] = s.cum_reward[e];
 }
