@@ -328,3 +328,33 @@ def test_numpy_api_skips_unchanged_window_blocks_without_changing_results():
     for k in o1:
         assert np.array_equal(o1[k], o2[k])
     e1.close(); e2.close()
+
+
+def test_draw_counter_overflow_fold():
+    """The per-env draw counter is a 12-bit field of the per-step state word, folded into the 64-bit counter of the
+    RNG record when it fills up: > 4095 draws per env must still count (and draw) exactly like the oracle, through a
+    get_state / set_state round trip and the roll-out kernel."""
+    import torch
+    kw = synthetic_kwargs(dict(scenario=2, operation="OP2"))
+    n, steps = 40, 4400
+    seeds = 3654 + np.arange(n)
+    ora = _oracle(kw, n, steps + 64, seeds)
+    env = make_env(kw, n, seed=3654)
+    ora.reset(); env.reset()
+    acts = np.empty((steps, n), dtype=np.int64)
+    acts[0::2], acts[1::2] = 0, 1                            # standby <-> cooldown: every step redraws the noise
+    for t in range(steps):
+        ora.step(acts[t])
+        if t == 4090:                                         # snapshot / restore right before the counter wraps
+            st = env.get_state()
+            assert st["draws"].min() > 4000
+            env.set_state(st)
+        env.step_tensor(torch.from_numpy(acts[t]).to(env.device))
+    _assert_state_equal(ora, env, "after the fold")
+    assert env.get_state()["draws"].min() > 4095
+    more = np.tile(np.array([[0], [1]], dtype=np.int64), (16, n))            # 32 more steps in one launch
+    env.rollout_tensor(torch.from_numpy(more).to(env.device))
+    for a in more:
+        ora.step(a)
+    _assert_state_equal(ora, env, "after the roll-out")
+    env.close(); ora.close()
