@@ -358,3 +358,44 @@ def test_draw_counter_overflow_fold():
         ora.step(a)
     _assert_state_equal(ora, env, "after the roll-out")
     env.close(); ora.close()
+
+
+def test_full_size_batch_through_an_episode_end():
+    """1 048 576 envs through one whole training episode (5 323 steps) and 200 steps beyond: every env ends its
+    episode exactly once, on the same step; the finished-episode statistics add up; and a window of global env ids
+    stepped as a small shard is bit-identical to the same ids inside the big batch -- across the auto-reset."""
+    import torch
+    kw = synthetic_kwargs(dict(scenario=2, operation="OP2"))
+    n_global = 1 << 20
+    ep_len = int(kw["eps_sim_steps"]) - 5
+    steps = ep_len + 200
+    lo, nw = 700_000, 1024
+
+    def run(n, offset):
+        env = make_env(kw, n, seed=3654, env_id_offset=offset, n_envs_global=n_global)
+        env.reset_tensor()
+        done_steps = torch.zeros(n, dtype=torch.int64, device=env.device)
+        n_done = torch.zeros(n, dtype=torch.int64, device=env.device)
+        rsum = torch.zeros(n, dtype=torch.float64, device=env.device)
+        for t in range(steps):
+            _, rew, done = env.step_tensor(_actions_by_global_id(t, offset, n, env.device))
+            d = done.to(torch.int64)
+            n_done += d
+            done_steps += d * t
+            rsum += rew.double()
+        out = (env.get_state(), n_done.cpu().numpy(), done_steps.cpu().numpy(), rsum.cpu().numpy(),
+               env.episode_stats(clear=True, reduce=False))
+        env.poll_error()
+        env.close()
+        return out
+
+    st, n_done, done_steps, rsum, stats = run(n_global, 0)
+    assert np.all(n_done == 1) and np.all(done_steps == ep_len - 1)
+    assert np.all(st["k"] == 200) and np.all(st["episode_count"] == 2)
+    assert stats["episodes"] == n_global and stats["length_mean"] == ep_len and stats["env_steps"] == n_global * steps
+    assert np.isfinite(rsum).all() and stats["return_min"] <= stats["return_mean"] <= stats["return_max"]
+    s2, nd2, ds2, rs2, _ = run(nw, lo)
+    for f in INT_FIELDS:
+        assert np.array_equal(s2[f], st[f][lo:lo + nw]), f"{f} differs in the window"
+    assert np.array_equal(rs2, rsum[lo:lo + nw]) and np.array_equal(nd2, n_done[lo:lo + nw])
+    assert np.array_equal(s2["cum_reward"], st["cum_reward"][lo:lo + nw])
