@@ -303,7 +303,11 @@ def run_gpu(args):
                                            "roofline_frac": frac_of(biased_ms, biased_draws)},
                        "sticky_policy": {"ms_per_step": sticky_ms, "draws_per_env_step": round(sticky_draws, 4),
                                          "roofline_frac": frac_of(sticky_ms, sticky_draws)},
-                       "rollout_kernel_ms_per_step": roll_ms, "episodes_finished": stats["episodes"]},
+                       "rollout_kernel": None if roll_ms is None else {
+                           "T": T, "ms_per_step": roll_ms,
+                           "bytes_per_env_step": round(bpe - 64 + 64 / T, 2),     # state stays in registers between steps
+                           "roofline_frac": (bpe - 64 + 64 / T) * n_local / (roll_ms * 1e-3) / 1e9 / peak},
+                       "episodes_finished": stats["episodes"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_step<4,true,false,false,13>",
                          "kernel_ms": kernel_ms},

@@ -12,7 +12,9 @@
  *     (e.g. torch tensors' data_ptr()); the library never frees them and keeps none past the call.
  *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*); no call synchronises the
  *     device except ptg_create / ptg_destroy / ptg_get_state / ptg_set_state / ptg_poll_error.
- *   - a handle is bound to one device and is not thread-safe.
+ *   - a handle is bound to one device and is not thread-safe.  ptg_step / ptg_step_many / the train-side entry
+ *     points launch on `stream` without touching the calling thread's current device: that device must be the
+ *     handle's (one process per GPU is the intended arrangement); ptg_create / ptg_reset / get / set_state select it.
  */
 #ifndef PTG_B200_H_
 #define PTG_B200_H_
