@@ -207,6 +207,7 @@ class PtGVecEnv(_Base):
         self._ev_scalars = torch.cuda.Event()
         self._scalar_off = 0 if obs_layout == "flat" else min(off for name, _, _, off in self.obs_keys
                                                                if name == "METH_STATUS")
+        self._status_elems = (n + 3) // 4 * 4     # padded length of one scalar block (16 B aligned block starts)
         self.bytes_per_env_step = int(self._L.ptg_bytes_per_env_step(self._h, _TORCH_ACT[act_dtype]))
         if seed is not None:
             self.seed(seed)
@@ -337,8 +338,14 @@ class PtGVecEnv(_Base):
         # the scalar blocks (METH_STATUS first) travel ahead of the window blocks, so the int64 conversion of
         # METH_STATUS overlaps the rest of the transfer
         cut = self._scalar_off
-        obs_h[cut:].copy_(self._obs[cut:], non_blocking=True)
+        if self.obs_layout == "flat":
+            obs_h.copy_(self._obs, non_blocking=True)
+        else:                                       # METH_STATUS block, then the other eight scalar blocks
+            mid = cut + int(self._status_elems)
+            obs_h[cut:mid].copy_(self._obs[cut:mid], non_blocking=True)
         self._ev_scalars.record(stream)
+        if self.obs_layout != "flat":
+            obs_h[mid:].copy_(self._obs[mid:], non_blocking=True)
         self.d2h_bytes += (obs_h.numel() - cut) * 4 + self.num_envs * 5 + 4
         eval_mode = bool(self.cfg.train_or_eval)
         if eval_mode:
