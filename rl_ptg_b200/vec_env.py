@@ -317,7 +317,10 @@ class PtGVecEnv(_Base):
             a = a.astype(np.float32, copy=False).reshape(self.num_envs)
         else:
             a = a.astype(np.int64, copy=False).reshape(self.num_envs)
-        self._act_h.numpy()[:] = a
+        if a.flags.c_contiguous and a.flags.writeable:
+            self._act_h.copy_(torch.from_numpy(a))          # torch's copy is multi-threaded for large arrays
+        else:
+            self._act_h.numpy()[:] = a
         self._act_d.copy_(self._act_h, non_blocking=True)
         if self.obs_layout != "flat":
             self._win_flag.zero_()
