@@ -399,3 +399,37 @@ def test_full_size_batch_through_an_episode_end():
         assert np.array_equal(s2[f], st[f][lo:lo + nw]), f"{f} differs in the window"
     assert np.array_equal(rs2, rsum[lo:lo + nw]) and np.array_equal(nd2, n_done[lo:lo + nw])
     assert np.array_equal(s2["cum_reward"], st["cum_reward"][lo:lo + nw])
+
+
+def test_single_env_gymnasium_interface_matches_reference_golden():
+    """rl_ptg_b200.gym_env.PTGEnv: the reference's single-env Gymnasium API (reset(seed) -> (obs, info),
+    step(a) -> (obs, reward, terminated, truncated, info)) against the golden eval-mode episode of ONE reference env."""
+    from helpers import golden_kwargs, load_golden
+    from rl_ptg_b200._abi import STATE_NAMES
+    from rl_ptg_b200.gym_env import PTGEnv
+    g = load_golden("bs2_op2_eval_test")
+    env = PTGEnv(golden_kwargs("bs2_op2_eval_test"), "eval")
+    obs, info = env.reset(seed=g["meta"]["seed"])
+    keys = g["meta"]["obs_keys"]
+    flat = lambda o: np.concatenate([np.atleast_1d(np.asarray(o[k], dtype=np.float64)).ravel() for k in keys])   # noqa: E731
+    assert_close_fp32(flat(obs), g["reset_obs"][0], "reset obs")
+    assert len(info) == 24 and info["Meth_Action"] in STATE_NAMES
+    keep = {int(t): q for q, t in enumerate(g["obs_steps"])}
+    term_step = int(g["term_steps"][0][0])
+    for t in range(term_step + 1):
+        obs, rew, terminated, truncated, info = env.step(int(g["actions"][t, 0]))
+        assert truncated is False and terminated == (t == term_step)
+        assert_close_fp32(np.float64(rew), g["rewards"][t, 0], f"reward step {t}")
+        if t % 97 == 0 or terminated:
+            row = np.array([float(STATE_NAMES.index(v)) if isinstance(v, str) else float(v) for v in list(info.values())[:24]])
+            assert np.allclose(row, g["infos"][t, 0], rtol=1e-9, atol=1e-12)
+            assert env.Meth_State == int(g["ints"][t, 0, 0]) or terminated
+        if terminated:
+            assert_close_fp32(flat(obs), g["term_obs"][0], "terminal obs")    # no auto-reset through this interface
+        elif t in keep:
+            assert_close_fp32(flat(obs), g["obs"][keep[t], 0], f"obs step {t}")
+    with pytest.raises(RuntimeError):
+        env.step(0)
+    obs, _ = env.reset()
+    assert obs["METH_STATUS"] == 1
+    env.close()
