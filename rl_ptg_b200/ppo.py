@@ -189,7 +189,9 @@ class PPO(PPOCore):
             self.gamma, self.gae_lambda, self.buf_adv, self.buf_ret)
         self.num_timesteps += self.n_steps * self.n_envs
 
-    def learn(self, total_timesteps: int, log_interval: int = 1):
+    def learn(self, total_timesteps: int, log_interval: int = 1, callback=None):
+        """``callback``: one callable or a list (e.g. ``EvalCallback``), called as ``cb(model)`` after every iteration."""
+        callbacks = [] if callback is None else (list(callback) if isinstance(callback, (list, tuple)) else [callback])
         t0 = time.perf_counter()
         it = 0
         while self.num_timesteps < total_timesteps:
@@ -204,6 +206,8 @@ class PPO(PPOCore):
                          env_reward_per_step=float(self._raw_reward_sum) / (self.n_steps * self.n_envs))
             self._raw_reward_sum.zero_()
             self.logs.append(stats)
+            for cb in callbacks:
+                cb(self)
         return self
 
     @torch.no_grad()
@@ -233,3 +237,30 @@ def reference_hyper_kwargs(h: dict | None = None) -> dict:
                 n_epochs=int(h["n_epoch"]), gamma=h["gamma"], gae_lambda=h["gae_lambda"],
                 normalize_advantage=h["normalize_advantage"], ent_coef=h["ent_coeff"],
                 hidden_layers=h["hidden_layers"], hidden_units=h["hidden_units"], activation=h["activation"])
+
+
+class EvalCallback:
+    """The role of SB3's ``EvalCallback`` as the reference sets it up (``src/rl_utils.py:456-469``): every
+    ``eval_freq`` timesteps, roll the deterministic policy out on an evaluation env (the ``n_envs`` of the reference's
+    ``eval_trials`` become the env's batch), log the mean return and keep the best policy's weights
+    (``best_model_save_path`` -> ``best_state_dict`` / an optional file)."""
+
+    def __init__(self, eval_env: PtGVecEnv, n_eval_steps: int, eval_freq: int, best_model_save_path: str | None = None,
+                 deterministic: bool = True):
+        self.eval_env, self.n_eval_steps, self.eval_freq = eval_env, int(n_eval_steps), int(eval_freq)
+        self.best_model_save_path, self.deterministic = best_model_save_path, deterministic
+        self.best_mean_reward, self.best_state_dict = -np.inf, None
+        self.evaluations: list[dict] = []
+        self._next = self.eval_freq
+
+    def __call__(self, model: "PPO") -> None:
+        if model.num_timesteps < self._next:
+            return
+        self._next = model.num_timesteps + self.eval_freq
+        ev = evaluate_policy(model, self.eval_env, self.n_eval_steps, self.deterministic)
+        self.evaluations.append(dict(timesteps=model.num_timesteps, **ev))
+        if ev["mean_cum_reward"] > self.best_mean_reward:
+            self.best_mean_reward = ev["mean_cum_reward"]
+            self.best_state_dict = {k: v.detach().clone() for k, v in model.policy.state_dict().items()}
+            if self.best_model_save_path:
+                torch.save(self.best_state_dict, self.best_model_save_path)

@@ -333,3 +333,19 @@ def test_calculate_optimum_on_device_is_bit_identical():
                                                price[f"eua_price_{m['split']}"], "set", list(STATS_NAMES), E)[k]
                         for k in STATS_NAMES], axis=1)
         assert np.array_equal(got, want[m["name"]])
+
+
+def test_eval_callback_keeps_the_best_policy():
+    from rl_ptg_b200.ppo import EvalCallback, PPO, reference_hyper_kwargs
+    from rl_ptg_b200.vec_env import PtGVecEnv
+    env = _env(1024, obs_layout="flat")
+    val = PtGVecEnv(synthetic_kwargs(dict(scenario=2, operation="OP2"), split="val"), 8, seed=605, obs_layout="flat")
+    hyper = reference_hyper_kwargs()
+    hyper.update(n_steps=16, batch_size=4096, n_epochs=2, learning_rate=3e-4, seed=0)
+    model = PPO(env, **hyper)
+    cb = EvalCallback(val, n_eval_steps=200, eval_freq=2 * 16 * 1024)
+    model.learn(6 * 16 * 1024, callback=cb)
+    assert len(cb.evaluations) == 3 and cb.best_state_dict is not None
+    assert cb.best_mean_reward == max(e["mean_cum_reward"] for e in cb.evaluations)
+    assert set(cb.best_state_dict) == set(model.policy.state_dict())
+    env.close(); val.close()
