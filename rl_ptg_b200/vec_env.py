@@ -394,7 +394,7 @@ class PtGVecEnv(_Base):
             if any_done and done_snap[e]:
                 d["episode"] = {"r": round(float(ret[e]), 6), "l": int(length[e]), "t": t_now}   # Monitor
                 d["TimeLimit.truncated"] = False                     # the env only ever terminates (:478-481)
-                d["terminal_observation"] = {k: v[e] for k, v in term.items()}
+                d["terminal_observation"] = {k: np.array(v[e]) for k, v in term.items()}     # (own copy)
             return d
 
         if lazy:
