@@ -335,17 +335,24 @@ def run_ppo_gpu(args):
     """PPO (SB3 algorithm, reference hyper-parameters except the roll-out geometry) with env, VecNormalize, feature
     rows and GAE on the device.  One "step" = one PPO iteration (collect n_steps x n_envs, then n_epochs of updates)."""
     import torch
+    import torch.distributed as dist
     from rl_ptg_b200.ppo import PPO, reference_hyper_kwargs
-    from rl_ptg_b200.vec_env import PtGVecEnv
+    from rl_ptg_b200.vec_env import PtGVecEnv, shard_range
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    if world > 1:           # data-parallel PPO: env shard + policy replica per rank, gradients averaged over NCCL
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     if args.ppo_tf32:                      # policy matmuls on the tensor cores (SB3's default is plain fp32)
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
     kw = make_kwargs()
     hyper = reference_hyper_kwargs()
     hyper.update(n_steps=args.ppo_n_steps, batch_size=args.ppo_batch, n_epochs=args.ppo_epochs, seed=3654)
-    env = PtGVecEnv(kw, args.ppo_envs, seed=3654, device=dev, obs_layout=args.ppo_layout)
+    n_global = args.ppo_envs * world
+    lo, hi = shard_range(n_global, rank, world)
+    env = PtGVecEnv(kw, hi - lo, seed=3654, device=dev, obs_layout=args.ppo_layout, env_id_offset=lo, n_envs_global=n_global)
     model = PPO(env, **hyper)
     per_iter = args.ppo_envs * args.ppo_n_steps
     model.learn(per_iter * max(1, args.warmup if args.warmup < 3 else 1))      # warm-up iteration(s): cuBLAS, allocator
@@ -363,11 +370,21 @@ def run_ppo_gpu(args):
     dt = time.perf_counter() - t0
     steps_done = model.num_timesteps - n0
     ep = env.episode_stats(clear=True, reduce=False)
-    _emit({"metric": PPO_METRIC, "value": steps_done / dt, "unit": UNIT, "n_gpus": 1, "steps": iters,
+    if world > 1:
+        t_all = torch.tensor([dt, tc], device=dev, dtype=torch.float64)
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        dt, tc = float(t_all[0]), float(t_all[1])
+        steps_done *= world
+        if rank != 0:
+            env.close()
+            dist.destroy_process_group()
+            return
+    _emit({"metric": PPO_METRIC, "value": steps_done / dt, "unit": UNIT, "n_gpus": world, "steps": iters,
            "warmup": 1, "ms_per_step": 1e3 * dt / iters, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": steps_done / dt / 166.6, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "PPO (MultiInputPolicy 2x358 ReLU) on BS2/OP2 mod, GPU VecEnv + VecNormalize + "
-                                  "feature rows + GAE on device", "n_envs": args.ppo_envs, "n_steps": args.ppo_n_steps,
+                                  "feature rows + GAE on device", "n_envs": args.ppo_envs * world, "n_steps": args.ppo_n_steps,
+                      "parallelism": f"dp{world}: env shard + policy replica per GPU, NCCL gradient all-reduce per mini-batch",
                       "batch_size": args.ppo_batch, "n_epochs": args.ppo_epochs,
                       "policy_matmul": "tf32" if args.ppo_tf32 else "fp32", "obs_layout": args.ppo_layout,
                       "collect_env_steps_per_s": steps_done / tc, "collect_share_of_time": tc / dt,
@@ -376,6 +393,8 @@ def run_ppo_gpu(args):
                       "episodes_finished": ep["episodes"], "ep_rew_mean": ep["return_mean"]},
            "gpu_launches": env.kernel_launches()})
     env.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_ppo_reference(args):

@@ -99,7 +99,7 @@ class PPOCore:
         self.normalize_advantage, self.ent_coef, self.vf_coef = normalize_advantage, ent_coef, vf_coef
         self.max_grad_norm = max_grad_norm
         if seed is not None:
-            torch.manual_seed(seed)
+            torch.manual_seed(seed)              # same initial policy on every rank
         self.continuous = continuous
         self.F = n_features
         self.policy = MultiInputActorCritic(self.F, 5, hidden_layers, hidden_units, activation,
@@ -116,6 +116,28 @@ class PPOCore:
         self.buf_ret = torch.empty((T, n), dtype=torch.float32, device=dev)
         self.num_timesteps = 0
         self.logs: list[dict] = []
+        # data-parallel training (one process per GPU, torch.distributed initialised): every rank collects from its
+        # own env shard and the gradients of each mini-batch are averaged over NCCL before the optimiser step
+        import torch.distributed as dist
+        self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self._world > 1:
+            for p_ in self.policy.parameters():
+                dist.broadcast(p_.data, src=0)
+            if seed is not None:
+                torch.manual_seed(seed + 7919 * (dist.get_rank() + 1))      # independent action sampling per rank
+
+    def _average_gradients(self):
+        if self._world == 1:
+            return
+        import torch.distributed as dist
+        grads = [p_.grad for p_ in self.policy.parameters() if p_.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        flat /= self._world
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
 
     def train(self):
         T, n = self.n_steps, self.n_envs
@@ -139,6 +161,7 @@ class PPOCore:
                 loss = pg_loss + self.ent_coef * ent_loss + self.vf_coef * v_loss
                 self.optimizer.zero_grad(set_to_none=True)
                 loss.backward()
+                self._average_gradients()
                 nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
                 self.optimizer.step()
                 pg_losses.append(pg_loss.detach()); v_losses.append(v_loss.detach()); ent_losses.append(ent_loss.detach())

@@ -59,3 +59,37 @@ def test_stats_allgather_combine_world2():
         assert out["return_min"] == 0.0 and out["return_max"] == 11.0 and out["length_mean"] == 35.0
         assert local["ranks"] == 1 and local["episodes"] == rank + 1
     assert results[0][0] == results[1][0]          # every rank computes the identical combined record
+
+
+def _ppo_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rl_ptg_b200.ppo import PPOCore
+        m = PPOCore(4, 40, "cpu", n_steps=8, batch_size=32, n_epochs=1, seed=5)
+        w0 = torch.cat([p.detach().reshape(-1) for p in m.policy.parameters()]).clone()
+        g = torch.Generator().manual_seed(100 + rank)             # different roll-out data on every rank
+        m.buf_feat.copy_(torch.randn(m.buf_feat.shape, generator=g))
+        m.buf_actions.copy_(torch.randint(0, 5, m.buf_actions.shape, generator=g))
+        m.buf_values.copy_(torch.randn(m.buf_values.shape, generator=g))
+        m.buf_logp.fill_(-1.6)
+        m.buf_adv.copy_(torch.randn(m.buf_adv.shape, generator=g))
+        m.buf_ret.copy_(torch.randn(m.buf_ret.shape, generator=g))
+        m.train()                                                 # one mini-batch: one averaged-gradient update
+        w1 = torch.cat([p.detach().reshape(-1) for p in m.policy.parameters()])
+        ret[rank] = (w0.numpy(), w1.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_ppo_keeps_replicas_identical():
+    """Data-parallel PPO (BASELINE config 5 on N GPUs): same initial policy on every rank, gradients of each
+    mini-batch averaged across ranks -> the replicas stay bit-identical although every rank sees different data."""
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_ppo_worker, args=(world, port, ret), nprocs=world, join=True)
+        results = dict(ret)
+    assert np.array_equal(results[0][0], results[1][0])           # broadcast initial weights
+    assert np.array_equal(results[0][1], results[1][1])           # identical after the averaged update
+    assert not np.array_equal(results[0][0], results[0][1])       # and the update did move them
