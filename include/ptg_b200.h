@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PTG_ABI_VERSION 1
+#define PTG_ABI_VERSION 2   /* 2: PtgConfig.obs_layout, PtgIO.windows_changed, train-side entry points */
 #define PTG_N_DATASETS 17
 #define PTG_N_INFO 24        /* fields of PTGEnv._get_info(), env/ptg_gym_env.py:251-278 */
 #define PTG_MAX_PRICE_AHEAD 16

@@ -12,7 +12,7 @@ import numpy as np
 
 from .config import OP_DATASETS
 
-PTG_ABI_VERSION = 1
+PTG_ABI_VERSION = 2
 PTG_N_DATASETS = 17
 PTG_N_INFO = 24
 PTG_MAX_PRICE_AHEAD = 16
