@@ -12,9 +12,10 @@
  *     (e.g. torch tensors' data_ptr()); the library never frees them and keeps none past the call.
  *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*); no call synchronises the
  *     device except ptg_create / ptg_destroy / ptg_get_state / ptg_set_state / ptg_poll_error.
- *   - a handle is bound to one device and is not thread-safe.  ptg_step / ptg_step_many / the train-side entry
- *     points launch on `stream` without touching the calling thread's current device: that device must be the
- *     handle's (one process per GPU is the intended arrangement); ptg_create / ptg_reset / get / set_state select it.
+ *   - a handle is bound to one device and is not thread-safe.  ptg_step / ptg_step_many / ptg_episode_stats /
+ *     ptg_allreduce_stats / the train-side entry points launch on `stream` without switching the calling thread's
+ *     current device: they return PTG_ERR_INVALID_ARGUMENT when that device is not the handle's (one process per GPU
+ *     is the intended arrangement); ptg_create / ptg_reset / get / set_state select the handle's device themselves.
  */
 #ifndef PTG_B200_H_
 #define PTG_B200_H_
@@ -25,7 +26,9 @@
 extern "C" {
 #endif
 
-#define PTG_ABI_VERSION 2   /* 2: PtgConfig.obs_layout, PtgIO.windows_changed, train-side entry points */
+#define PTG_ABI_VERSION 3   /* 2: PtgConfig.obs_layout, PtgIO.windows_changed, train-side entry points
+                               3: PtgStateSoA.rng / .state_changes, PtgConfig.no_auto_reset, windows_changed carries the step serial,
+                                  ptg_allreduce_stats + ptg_nccl_* (cross-rank statistics inside the library) */
 #define PTG_N_DATASETS 17
 #define PTG_N_INFO 24        /* fields of PTGEnv._get_info(), env/ptg_gym_env.py:251-278 */
 #define PTG_MAX_PRICE_AHEAD 16
@@ -50,7 +53,7 @@ typedef enum PtgStatus {
     PTG_ERR_INVALID_ACTION = -4,     /* device saw an action outside 0..4 (reference: ptg_gym_env.py:347,440) */
     PTG_ERR_DATA_RANGE = -5,         /* device indexed past the market tables (reference: IndexError) */
     PTG_ERR_NOISE_TAPE = -6,         /* tape-mode noise ran past the end of the tape */
-    PTG_ERR_NCCL = -7
+    PTG_ERR_NCCL = -7                /* libnccl.so.2 could not be loaded, or an NCCL call failed (ptg_nccl_*, ptg_allreduce_stats) */
 } PtgStatus;
 
 enum PtgActionDtype { PTG_ACT_I64 = 0, PTG_ACT_I32 = 1, PTG_ACT_U8 = 2, PTG_ACT_F32 = 3 };
@@ -100,6 +103,10 @@ typedef struct PtgConfig {
             time5_f_p_f;
     int32_t i_fully_developed, j_fully_developed;
     int32_t obs_layout;             /* PtgObsLayout: 0 = key-major blocks (default), 1 = flat feature rows */
+    int32_t no_auto_reset;          /* 0 (default) = SB3 VecEnv semantics: a done env is reset inside the step (the
+                                       returned obs is the reset obs).  1 = Gymnasium single-env semantics
+                                       (env/ptg_gym_env.py:476-481): the returned obs is the terminal obs and the env
+                                       stays as it is until ptg_reset -- which alone consumes the next eps_ind entry */
     double noise;                   /* sigma [rows] */
     double eps_len_d;               /* [d] */
     double state_change_penalty;
@@ -139,12 +146,14 @@ typedef struct PtgIO {
                                 info (SB3 keeps the pre-reset info). Meth_Action is the action id 0..4. */
     double* episode_return;  /* [n_envs] Monitor-style sum of returned rewards of the episode that just ended */
     int32_t* episode_length; /* [n_envs] its length; both written only where done=1; NULL allowed */
-    uint32_t* windows_changed; /* one word or NULL (ptg_step, key-major layout): set to 1 when the step changed any
-                                  env's market-window blocks (Pot_Reward / Part_Full / Elec_Price / Gas_Price /
-                                  EUA_Price): they only move when an env's clock crosses an hour or its episode
-                                  ends, i.e. on one step in 3600 / sim_step.  Never cleared by the library: a
-                                  host mirror that zeroes it before the step may skip the transfer of those blocks
-                                  (3/4 of the observation bytes) when it still reads 0. */
+    uint32_t* windows_changed; /* one word or NULL (ptg_step, key-major layout): when the step changed any env's
+                                  market-window blocks (Pot_Reward / Part_Full / Elec_Price / Gas_Price / EUA_Price)
+                                  the kernel stores the step's serial number here (ptg_last_step_serial() right after
+                                  the call; never 0).  The blocks only move when an env's clock crosses an hour or its
+                                  episode ends, i.e. on one step in 3600 / sim_step.  The library never clears the
+                                  word and the caller does not have to: a host mirror that finds a value other than
+                                  the serial of the step it just issued may skip the transfer of those blocks (3/4 of
+                                  the observation bytes). */
 } PtgIO;
 
 /* One observation key of the obs buffer. */
@@ -196,8 +205,9 @@ int ptg_step_many(PtgHandle* h, const void* actions, int action_dtype, int32_t T
 /* Tape-mode noise: device fp64 [n_envs][tape_len], values as returned by normal(0, noise) (already scaled). */
 int ptg_set_noise_tape(PtgHandle* h, const double* tape_dev, int64_t tape_len);
 
-/* Plant state snapshot (host SoA arrays of n_envs each; any pointer may be NULL).  Used by parity tests and
- * checkpointing (the reference never checkpoints env state). */
+/* Plant state snapshot (host SoA arrays of n_envs each; any pointer may be NULL in ptg_get_state, none in
+ * ptg_set_state).  Used by parity tests and checkpointing (the reference never checkpoints env state): a restored
+ * env continues bit-identically, noise stream included. */
 typedef struct PtgStateSoA {
     int32_t* meth_state;     /* Meth_State */
     int32_t* i;              /* row index i */
@@ -215,6 +225,8 @@ typedef struct PtgStateSoA {
     int64_t* draws;          /* noise values consumed so far (tape position) */
     double* t_cat;           /* Meth_T_cat */
     double* cum_reward;      /* Monitor-style running return (== cum_rew when state_change_penalty == 0) */
+    uint64_t* rng;           /* [n_envs][4]: the env's PCG64 generator {state_hi, state_lo, inc_hi, inc_lo} (np_random) */
+    uint32_t* state_changes; /* Meth_State changes this episode (info cum_reward = cum_reward + penalty * this) */
 } PtgStateSoA;
 int ptg_get_state(PtgHandle* h, const PtgStateSoA* out);
 int ptg_set_state(PtgHandle* h, const PtgStateSoA* in);
@@ -225,6 +237,23 @@ int ptg_episode_stats(PtgHandle* h, PtgEpisodeStats* stats_dev, int clear, void*
 
 /* Host-side combine of per-rank stats (sum / min / max), e.g. after an NCCL all-gather of the 64-byte structs. */
 void ptg_stats_combine(const PtgEpisodeStats* per_rank, int n_ranks, PtgEpisodeStats* out);
+
+/* Cross-rank reduction of the episode statistics inside the library (the path's ONLY collective):
+ * ncclAllGather of the 64-byte record over `nccl_comm` (an ncclComm_t as void*; one process per GPU, NVLink/NVSwitch)
+ * followed by a fixed-rank-order combine kernel, everything on `stream`, no host synchronisation.  On return (in
+ * stream order) *stats_dev -- this rank's record from ptg_episode_stats -- holds the combined record on every rank.
+ * Replaces what SB3's Monitor/logger do with per-env episode records in one process (rollout/ep_rew_mean). */
+int ptg_allreduce_stats(PtgHandle* h, void* nccl_comm, PtgEpisodeStats* stats_dev, void* stream);
+
+/* NCCL plumbing for binders that have no communicator of their own.  libnccl.so.2 is dlopen()ed on first use (the one
+ * already in the process if any -- e.g. the torch wheel's -- so there are never two NCCLs in one process).
+ *   ptg_nccl_unique_id   : rank 0 creates the 128-byte id and ships it to the others by any side channel
+ *   ptg_nccl_comm_create : every rank, with the handle's device current; *comm_out is an ncclComm_t
+ *   ptg_nccl_comm_destroy */
+#define PTG_NCCL_UNIQUE_ID_BYTES 128
+int ptg_nccl_unique_id(char id_out[PTG_NCCL_UNIQUE_ID_BYTES]);
+int ptg_nccl_comm_create(const char id[PTG_NCCL_UNIQUE_ID_BYTES], int n_ranks, int rank, void** comm_out);
+int ptg_nccl_comm_destroy(void* comm);
 
 /* ---- callers either side of the path; all pointers are device memory unless noted ----------- */
 
@@ -286,6 +315,7 @@ int64_t ptg_obs_elems(const PtgHandle* h);                       /* fp32 element
 int64_t ptg_num_envs(const PtgHandle* h);
 int64_t ptg_bytes_per_env_step(const PtgHandle* h, int action_dtype);    /* algorithmic HBM bytes, DESIGN.md */
 int ptg_kernel_launches(const PtgHandle* h, int64_t* out);               /* kernels launched by this handle */
+uint32_t ptg_last_step_serial(const PtgHandle* h);                       /* serial of the latest ptg_step (see PtgIO.windows_changed) */
 /* Host twins of the on-device generator (no GPU needed): the first n values of
  * Generator(PCG64(SeedSequence(seed))).standard_normal() -- bit-identical to numpy; used by the CPU test-suite. */
 int ptg_host_standard_normal(uint64_t seed, int64_t n, double* out);

@@ -21,7 +21,19 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("PTG_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED_ROOT = os.path.join(_REPO, "baseline", "_ref")      # tools/stage_reference.sh: travels to the GPU box
+
+
+def _default_root() -> str:
+    """The mounted checkout in the build container, else the staged copy (the only one a GPU box has)."""
+    for cand in (os.environ.get("PTG_REFERENCE_ROOT"), "/root/reference", STAGED_ROOT):
+        if cand and os.path.isfile(os.path.join(cand, "env", "ptg_gym_env.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _default_root()
 
 
 def reference_available() -> bool:

@@ -12,10 +12,11 @@ import numpy as np
 
 from .config import OP_DATASETS
 
-PTG_ABI_VERSION = 2
+PTG_ABI_VERSION = 3
 PTG_N_DATASETS = 17
 PTG_N_INFO = 24
 PTG_MAX_PRICE_AHEAD = 16
+PTG_NCCL_UNIQUE_ID_BYTES = 128
 
 DATASET_NAMES = tuple(k for k, _ in OP_DATASETS)        # index == enum PtgDataset
 STATE_NAMES = ("standby", "cooldown", "startup", "partial_load", "full_load")   # index == state/action id
@@ -45,7 +46,7 @@ _I32_FIELDS = (
     "time5_p_f_p",
     "time1_f_p_f", "time2_f_p_f", "time23_f_p_f", "time3_f_p_f", "time34_f_p_f", "time4_f_p_f", "time45_f_p_f",
     "time5_f_p_f",
-    "i_fully_developed", "j_fully_developed", "obs_layout",
+    "i_fully_developed", "j_fully_developed", "obs_layout", "no_auto_reset",
 )
 _F64_FIELDS = (
     "noise", "eps_len_d", "state_change_penalty", "reward_level",
@@ -102,16 +103,23 @@ _STATE_I32 = ("meth_state", "i", "j", "k", "hot_cold", "standby_ds", "startup_ds
 
 class PtgStateSoA(C.Structure):
     _fields_ = [(f, C.c_void_p) for f in _STATE_I32] + [("draws", C.c_void_p), ("t_cat", C.c_void_p),
-                                                        ("cum_reward", C.c_void_p)]
+                                                        ("cum_reward", C.c_void_p), ("rng", C.c_void_p),
+                                                        ("state_changes", C.c_void_p)]
 
 
 STATE_FIELDS = tuple((f, np.int32) for f in _STATE_I32) + (("draws", np.int64), ("t_cat", np.float64),
-                                                           ("cum_reward", np.float64))
+                                                           ("cum_reward", np.float64), ("rng", np.uint64),
+                                                           ("state_changes", np.uint32))
+STATE_WIDTH = {"rng": 4}        # fields with more than one value per env: rng = PCG64 {state_hi, state_lo, inc_hi, inc_lo}
+
+
+def state_shape(name: str, n_envs: int) -> tuple:
+    return (n_envs, STATE_WIDTH[name]) if name in STATE_WIDTH else (n_envs,)
 
 
 def alloc_state(n_envs: int):
     """Host arrays + the struct pointing at them."""
-    arrays = {name: np.zeros(n_envs, dtype=dt) for name, dt in STATE_FIELDS}
+    arrays = {name: np.zeros(state_shape(name, n_envs), dtype=dt) for name, dt in STATE_FIELDS}
     s = PtgStateSoA()
     for name, _ in STATE_FIELDS:
         setattr(s, name, arrays[name].ctypes.data)
@@ -126,7 +134,7 @@ def _as_int(name: str, v) -> int:
 
 
 def config_from_kwargs(dict_input: dict, train_or_eval: str = "train", noise_mode: int = NOISE_NUMPY,
-                       schedule_mode: int | None = None, obs_layout: int = 0) -> PtgConfig:
+                       schedule_mode: int | None = None, obs_layout: int = 0, auto_reset: bool = True) -> PtgConfig:
     """Validate the reference constructor dict and pack its scalars."""
     d = dict_input
     if train_or_eval not in ("train", "eval"):
@@ -154,6 +162,7 @@ def config_from_kwargs(dict_input: dict, train_or_eval: str = "train", noise_mod
         schedule_mode = SCHED_SUBPROC if d.get("parallel") == "Multiprocessing" else SCHED_DUMMY
     cfg.schedule_mode = schedule_mode
     cfg.obs_layout = int(obs_layout)
+    cfg.no_auto_reset = 0 if auto_reset else 1
     cfg.n_eps_loops = max(1, int(d.get("n_eps_loops", 1) or 1))
     for k in _TIME_KEYS:
         setattr(cfg, k, _as_int(k, d[k]))

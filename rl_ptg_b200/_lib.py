@@ -17,7 +17,8 @@ EXPORTS = (
     "ptg_obs_elems", "ptg_num_envs", "ptg_bytes_per_env_step", "ptg_kernel_launches", "ptg_host_standard_normal",
     "ptg_host_seed_state", "ptg_last_error",
     "ptg_abi_version", "ptg_vecnorm_moments", "ptg_vecnorm_apply", "ptg_features_dim", "ptg_features", "ptg_gae",
-    "ptg_calculate_optimum",
+    "ptg_calculate_optimum", "ptg_allreduce_stats", "ptg_nccl_unique_id", "ptg_nccl_comm_create",
+    "ptg_nccl_comm_destroy", "ptg_last_step_serial",
 )
 
 
@@ -57,6 +58,12 @@ def load(build_if_missing: bool = False):
     L.ptg_stats_combine.argtypes = [C.POINTER(_abi.PtgEpisodeStats), i32, C.POINTER(_abi.PtgEpisodeStats)]
     L.ptg_stats_combine.restype = None
     L.ptg_poll_error.argtypes = [vp, vp]
+    L.ptg_allreduce_stats.argtypes = [vp, vp, vp, vp]
+    L.ptg_nccl_unique_id.argtypes = [C.c_char_p]
+    L.ptg_nccl_comm_create.argtypes = [C.c_char_p, i32, i32, C.POINTER(vp)]
+    L.ptg_nccl_comm_destroy.argtypes = [vp]
+    L.ptg_last_step_serial.argtypes = [vp]
+    L.ptg_last_step_serial.restype = C.c_uint32
     f64 = C.c_double
     L.ptg_vecnorm_moments.argtypes = [vp, vp, vp, f64, vp, vp, vp]
     L.ptg_vecnorm_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, f64, f64, vp, vp]

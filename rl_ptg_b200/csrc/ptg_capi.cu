@@ -1,4 +1,6 @@
 // ptg_capi.cu -- host side of libptg_b200.so: the C ABI declared in include/ptg_b200.h.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -45,9 +47,13 @@ struct PtgHandle {
     Sums* d_vn_partial = nullptr;     // per-CTA partial sums of the VecNormalize returns
     unsigned int* d_vn_ticket = nullptr;
     uint32_t* d_err = nullptr;
-    int32_t* d_state_i32 = nullptr;   // scratch for get/set state: 13 int32 arrays
+    int32_t* d_state_i32 = nullptr;   // scratch for get/set state: 13 int32 arrays + state_changes
     int64_t* d_state_i64 = nullptr;
     double* d_state_f64 = nullptr;    // 2 arrays
+    uint64_t* d_state_rng = nullptr;  // [n][4]
+    PtgEpisodeStats* d_gather = nullptr;   // all-gather target of ptg_allreduce_stats
+    int gather_ranks = 0;
+    uint32_t step_serial = 0;
     int64_t launches = 0;
     double total_steps = 0.0;
 
@@ -76,8 +82,8 @@ namespace {
 // Step kernels are launched with programmatic stream serialization (PDL): back-to-back steps overlap the next
 // launch's prologue with the current launch's tail wave (the kernel does griddepcontrol.wait before it reads state).
 template <typename K>
-void launch_pdl(K kernel, unsigned grid, cudaStream_t st, const DevParams& P, const void* actions, int adtype,
-                const PtgIO& io, int T) {
+cudaError_t launch_pdl(K kernel, unsigned grid, cudaStream_t st, const DevParams& P, const void* actions, int adtype,
+                       const PtgIO& io, int T) {
 #if PTG_PDL
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -89,14 +95,15 @@ void launch_pdl(K kernel, unsigned grid, cudaStream_t st, const DevParams& P, co
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, P, actions, adtype, io, T);
+    return cudaLaunchKernelEx(&cfg, kernel, P, actions, adtype, io, T);
 #else
     kernel<<<grid, PTG_BLOCK, 0, st>>>(P, actions, adtype, io, T);
+    return cudaGetLastError();
 #endif
 }
 
 template <int NV, bool MOD>
-void launch_step_t(PtgHandle* h, const void* actions, int adtype, const PtgIO& io, int T, cudaStream_t st) {
+cudaError_t launch_step_t(PtgHandle* h, const void* actions, int adtype, const PtgIO& io, int T, cudaStream_t st) {
     unsigned grid = blocks_for(h->P.n_envs, PTG_BLOCK);
     if (h->P.flat && T == 0)   // single steps of the flat layout: persistent CTAs, one scheduling wave of them (see k_step)
         grid = std::min<unsigned>(grid, (unsigned)std::max(1, h->P.prefetch_distance / PTG_BLOCK));
@@ -104,35 +111,48 @@ void launch_step_t(PtgHandle* h, const void* actions, int adtype, const PtgIO& i
     const bool pa13 = NV == 4 && h->P.pa == 13;       // compile-time price_ahead for the reference default
     constexpr int P13 = NV == 4 ? 13 : 0;
     if (h->P.flat) {                                  // (validated at create: price_ahead == 13, train mode)
-        if (T > 0) launch_pdl(k_step<4, MOD, true, false, 13, true>, grid, st, h->P, actions, adtype, io, T);
-        else launch_pdl(k_step<4, MOD, false, false, 13, true>, grid, st, h->P, actions, adtype, io, 1);
+        if (T > 0) return launch_pdl(k_step<4, MOD, true, false, 13, true>, grid, st, h->P, actions, adtype, io, T);
+        return launch_pdl(k_step<4, MOD, false, false, 13, true>, grid, st, h->P, actions, adtype, io, 1);
     } else if (T > 0) {
-        if (pa13) launch_pdl(k_step<NV, MOD, true, false, P13>, grid, st, h->P, actions, adtype, io, T);
-        else launch_pdl(k_step<NV, MOD, true, false, 0>, grid, st, h->P, actions, adtype, io, T);
+        if (pa13) return launch_pdl(k_step<NV, MOD, true, false, P13>, grid, st, h->P, actions, adtype, io, T);
+        return launch_pdl(k_step<NV, MOD, true, false, 0>, grid, st, h->P, actions, adtype, io, T);
     } else if (h->P.eval_mode && io.info) {
-        launch_pdl(k_step<NV, MOD, false, true, 0>, grid, st, h->P, actions, adtype, io, 1);
-    } else {
-        if (pa13) launch_pdl(k_step<NV, MOD, false, false, P13>, grid, st, h->P, actions, adtype, io, 1);
-        else launch_pdl(k_step<NV, MOD, false, false, 0>, grid, st, h->P, actions, adtype, io, 1);
+        return launch_pdl(k_step<NV, MOD, false, true, 0>, grid, st, h->P, actions, adtype, io, 1);
     }
+    if (pa13) return launch_pdl(k_step<NV, MOD, false, false, P13>, grid, st, h->P, actions, adtype, io, 1);
+    return launch_pdl(k_step<NV, MOD, false, false, 0>, grid, st, h->P, actions, adtype, io, 1);
 }
 template <int NV, bool MOD>
-void launch_reset_t(PtgHandle* h, const int64_t* seeds, const uint8_t* mask, const PtgIO& io, cudaStream_t st) {
+cudaError_t launch_reset_t(PtgHandle* h, const int64_t* seeds, const uint8_t* mask, const PtgIO& io, cudaStream_t st) {
     if (h->P.flat) k_reset<4, MOD, true><<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, 0, st>>>(h->P, seeds, mask, io);
     else k_reset<NV, MOD><<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, 0, st>>>(h->P, seeds, mask, io);
+    return cudaGetLastError();
 }
 
-#define PTG_DISPATCH(fn, ...)                                                     \
+#define PTG_DISPATCH(err, fn, ...)                                                \
     do {                                                                          \
         const bool mod__ = !h->P.raw;                                             \
         switch (h->P.nv) {                                                        \
-            case 1: mod__ ? fn<1, true>(__VA_ARGS__) : fn<1, false>(__VA_ARGS__); break; \
-            case 2: mod__ ? fn<2, true>(__VA_ARGS__) : fn<2, false>(__VA_ARGS__); break; \
-            case 3: mod__ ? fn<3, true>(__VA_ARGS__) : fn<3, false>(__VA_ARGS__); break; \
-            case 4: mod__ ? fn<4, true>(__VA_ARGS__) : fn<4, false>(__VA_ARGS__); break; \
-            default: mod__ ? fn<5, true>(__VA_ARGS__) : fn<5, false>(__VA_ARGS__); break; \
+            case 1: err = mod__ ? fn<1, true>(__VA_ARGS__) : fn<1, false>(__VA_ARGS__); break; \
+            case 2: err = mod__ ? fn<2, true>(__VA_ARGS__) : fn<2, false>(__VA_ARGS__); break; \
+            case 3: err = mod__ ? fn<3, true>(__VA_ARGS__) : fn<3, false>(__VA_ARGS__); break; \
+            case 4: err = mod__ ? fn<4, true>(__VA_ARGS__) : fn<4, false>(__VA_ARGS__); break; \
+            default: err = mod__ ? fn<5, true>(__VA_ARGS__) : fn<5, false>(__VA_ARGS__); break; \
         }                                                                         \
     } while (0)
+
+// The hot entry points launch on the caller's stream without switching devices: refuse a foreign current device
+// instead of failing later with an opaque invalid-resource-handle error.
+int check_device(const PtgHandle* h, const char* what) {
+    int cur = -1;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return fail(PTG_ERR_CUDA, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+    if (cur != h->device)
+        return fail(PTG_ERR_INVALID_ARGUMENT, std::string(what) + ": the calling thread's current CUDA device (" +
+                    std::to_string(cur) + ") is not the handle's (" + std::to_string(h->device) +
+                    "); call cudaSetDevice first (one process per GPU is the intended arrangement)");
+    return PTG_OK;
+}
 
 int validate(const PtgConfig* c, const PtgTables* t, int64_t n_envs, int64_t off, int64_t n_global) {
     if (!c || !t) return fail(PTG_ERR_INVALID_ARGUMENT, "null config/tables");
@@ -145,6 +165,7 @@ int validate(const PtgConfig* c, const PtgTables* t, int64_t n_envs, int64_t off
     if (c->obs_layout != PTG_OBS_KEY_MAJOR && c->obs_layout != PTG_OBS_FLAT) return fail(PTG_ERR_INVALID_ARGUMENT, "obs_layout out of range");
     if (c->obs_layout == PTG_OBS_FLAT && (c->price_ahead != 13 || c->train_or_eval != 0))
         return fail(PTG_ERR_UNSUPPORTED, "the flat observation layout is built for price_ahead == 13 and train_or_eval = train");
+    if (c->no_auto_reset != 0 && c->no_auto_reset != 1) return fail(PTG_ERR_INVALID_ARGUMENT, "no_auto_reset must be 0 or 1");
     if (c->schedule_mode < 0 || c->schedule_mode > 1) return fail(PTG_ERR_INVALID_ARGUMENT, "schedule_mode out of range");
     if (c->price_ahead < 1) return fail(PTG_ERR_INVALID_ARGUMENT, "price_ahead must be >= 1");
     if (c->price_ahead > PTG_MAX_PRICE_AHEAD) return fail(PTG_ERR_UNSUPPORTED, "price_ahead > 16 is not supported by the packed hour row");
@@ -217,6 +238,7 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     P.schedule_mode = c.schedule_mode;
     P.penalty = c.reward_level * c.state_change_penalty;                       // :332
     P.has_penalty = P.penalty != 0.0;
+    P.auto_reset = c.no_auto_reset ? 0 : 1;
     P.i_fully_developed = c.i_fully_developed; P.j_fully_developed = c.j_fully_developed;
     P.noise = c.noise; P.eps_len_d = c.eps_len_d;
     RewardConsts& R = P.rc;
@@ -415,7 +437,7 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     const size_t n = (size_t)n_envs;
     PTG_TRY(h->alloc(&P.core, n)); PTG_TRY(h->alloc(&P.tinfo, n)); PTG_TRY(h->alloc(&P.ep, n));
     PTG_TRY(h->alloc(&P.ep_ret, n)); PTG_TRY(h->alloc(&P.ep_count, n)); PTG_TRY(h->alloc(&P.ep_start, n));
-    PTG_TRY(h->alloc(&P.nchg, n)); PTG_TRY(h->alloc(&P.rng, n));
+    PTG_TRY(h->alloc(&P.nchg, n)); PTG_TRY(h->alloc(&P.rng, n)); PTG_TRY(h->alloc(&P.draws_total, n));
     PTG_TRY(h->alloc(&P.fin_cnt, n)); PTG_TRY(h->alloc(&P.fin_ret_sum, n)); PTG_TRY(h->alloc(&P.fin_ret_sq, n));
     PTG_TRY(h->alloc(&P.fin_len_sum, n)); PTG_TRY(h->alloc(&P.fin_min, n)); PTG_TRY(h->alloc(&P.fin_max, n));
     PTG_TRY(h->alloc(&h->d_seeds, n)); PTG_TRY(h->alloc(&h->d_mask, n));
@@ -423,7 +445,8 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     PTG_TRY(h->alloc(&h->d_vn_partial, PTG_STATS_BLOCKS));
     PTG_TRY(h->alloc(&h->d_vn_ticket, 1));
     PTG_TRY(cudaMemset(h->d_vn_ticket, 0, sizeof(unsigned int)));
-    PTG_TRY(h->alloc(&h->d_state_i32, n * 13)); PTG_TRY(h->alloc(&h->d_state_i64, n)); PTG_TRY(h->alloc(&h->d_state_f64, n * 2));
+    PTG_TRY(h->alloc(&h->d_state_i32, n * 14)); PTG_TRY(h->alloc(&h->d_state_i64, n)); PTG_TRY(h->alloc(&h->d_state_f64, n * 2));
+    PTG_TRY(h->alloc(&h->d_state_rng, n * 4));
     P.tape = nullptr; P.tape_len = 0;
     {   // one scheduling wave = resident CTAs of the step kernel on this device
         cudaDeviceProp prop{};
@@ -467,9 +490,10 @@ extern "C" int ptg_reset(PtgHandle* h, const int64_t* seeds, const uint8_t* mask
         PTG_CUDA(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, st));
         d_mask = h->d_mask;
     }
-    PTG_DISPATCH(launch_reset_t, h, d_seeds, d_mask, *io, st);
+    cudaError_t lerr = cudaSuccess;
+    PTG_DISPATCH(lerr, launch_reset_t, h, d_seeds, d_mask, *io, st);
     h->launches += 1;
-    PTG_CUDA(cudaGetLastError());
+    PTG_CUDA(lerr);
     return PTG_OK;
 }
 
@@ -479,17 +503,20 @@ static int check_step_io(const PtgHandle* h, const void* actions, int adtype, co
     if (adtype < PTG_ACT_I64 || adtype > PTG_ACT_F32) return fail(PTG_ERR_INVALID_ARGUMENT, "unknown action dtype");
     if (h->P.continuous && adtype != PTG_ACT_F32)
         return fail(PTG_ERR_INVALID_ARGUMENT, "continuous action space needs float32 actions (Box(-1, 1, (1,), float32))");
-    return PTG_OK;
+    return check_device(h, "ptg_step");
 }
 
 extern "C" int ptg_step(PtgHandle* h, const void* actions, int action_dtype, const PtgIO* io, void* stream) {
     int rc = check_step_io(h, actions, action_dtype, io);
     if (rc != PTG_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PTG_DISPATCH(launch_step_t, h, actions, action_dtype, *io, 0, st);
+    if (++h->step_serial == 0) h->step_serial = 1;          // (never 0: see PtgIO.windows_changed)
+    h->P.step_serial = h->step_serial;
+    cudaError_t lerr = cudaSuccess;
+    PTG_DISPATCH(lerr, launch_step_t, h, actions, action_dtype, *io, 0, st);
     h->launches += 1;
     h->total_steps += (double)h->P.n_envs;
-    PTG_CUDA(cudaGetLastError());
+    PTG_CUDA(lerr);
     return PTG_OK;
 }
 
@@ -500,11 +527,13 @@ extern "C" int ptg_step_many(PtgHandle* h, const void* actions, int action_dtype
     if (T < 1) return fail(PTG_ERR_INVALID_ARGUMENT, "T must be >= 1");
     if (io->terminal_obs || io->info || io->episode_return || io->episode_length)
         return fail(PTG_ERR_INVALID_ARGUMENT, "ptg_step_many records only obs/reward/done");
+    if (!h->P.auto_reset) return fail(PTG_ERR_INVALID_ARGUMENT, "ptg_step_many needs auto-reset (PtgConfig.no_auto_reset = 0)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    PTG_DISPATCH(launch_step_t, h, actions, action_dtype, *io, (int)T, st);
+    cudaError_t lerr = cudaSuccess;
+    PTG_DISPATCH(lerr, launch_step_t, h, actions, action_dtype, *io, (int)T, st);
     h->launches += 1;
     h->total_steps += (double)h->P.n_envs * T;
-    PTG_CUDA(cudaGetLastError());
+    PTG_CUDA(lerr);
     return PTG_OK;
 }
 
@@ -527,6 +556,7 @@ static StateDev state_dev(PtgHandle* h) {
     s.startup_ds = b + 6 * n; s.partial_ds = b + 7 * n; s.full_ds = b + 8 * n; s.current_action = b + 9 * n;
     s.act_ep_h = b + 10 * n; s.act_ep_d = b + 11 * n; s.episode_count = b + 12 * n;
     s.draws = h->d_state_i64; s.t_cat = h->d_state_f64; s.cum_reward = h->d_state_f64 + n;
+    s.rng = h->d_state_rng; s.state_changes = reinterpret_cast<uint32_t*>(b + 13 * n);
     return s;
 }
 
@@ -547,6 +577,8 @@ extern "C" int ptg_get_state(PtgHandle* h, const PtgStateSoA* out) {
     if (out->draws) PTG_CUDA(cudaMemcpy(out->draws, s.draws, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
     if (out->t_cat) PTG_CUDA(cudaMemcpy(out->t_cat, s.t_cat, n * sizeof(double), cudaMemcpyDeviceToHost));
     if (out->cum_reward) PTG_CUDA(cudaMemcpy(out->cum_reward, s.cum_reward, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (out->rng) PTG_CUDA(cudaMemcpy(out->rng, s.rng, n * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (out->state_changes) PTG_CUDA(cudaMemcpy(out->state_changes, s.state_changes, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return PTG_OK;
 }
 
@@ -556,7 +588,8 @@ extern "C" int ptg_set_state(PtgHandle* h, const PtgStateSoA* in) {
                                       in->partial_ds, in->full_ds, in->current_action, in->act_ep_h, in->act_ep_d,
                                       in->episode_count};
     for (int q = 0; q < 13; ++q) if (!src32[q]) return fail(PTG_ERR_INVALID_ARGUMENT, "ptg_set_state needs every field");
-    if (!in->draws || !in->t_cat || !in->cum_reward) return fail(PTG_ERR_INVALID_ARGUMENT, "ptg_set_state needs every field");
+    if (!in->draws || !in->t_cat || !in->cum_reward || !in->rng || !in->state_changes)
+        return fail(PTG_ERR_INVALID_ARGUMENT, "ptg_set_state needs every field");
     PTG_CUDA(cudaSetDevice(h->device));
     PTG_CUDA(cudaDeviceSynchronize());
     StateDev s = state_dev(h);
@@ -572,6 +605,8 @@ extern "C" int ptg_set_state(PtgHandle* h, const PtgStateSoA* in) {
     PTG_CUDA(cudaMemcpy(s.draws, in->draws, n * sizeof(int64_t), cudaMemcpyHostToDevice));
     PTG_CUDA(cudaMemcpy(s.t_cat, in->t_cat, n * sizeof(double), cudaMemcpyHostToDevice));
     PTG_CUDA(cudaMemcpy(s.cum_reward, in->cum_reward, n * sizeof(double), cudaMemcpyHostToDevice));
+    PTG_CUDA(cudaMemcpy(s.rng, in->rng, n * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    PTG_CUDA(cudaMemcpy(s.state_changes, in->state_changes, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     k_state_pack<<<blocks_for(h->P.n_envs, 256), 256>>>(h->P, s, h->B);
     h->launches += 1;
     PTG_CUDA(cudaDeviceSynchronize());
@@ -584,11 +619,130 @@ extern "C" int ptg_set_state(PtgHandle* h, const PtgStateSoA* in) {
 // ------------------------------------------------------------------------------------------------------------
 extern "C" int ptg_episode_stats(PtgHandle* h, PtgEpisodeStats* stats_dev, int clear, void* stream) {
     if (!h || !stats_dev) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle/stats");
+    int rc = check_device(h, "ptg_episode_stats");
+    if (rc != PTG_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     k_stats_partial<<<PTG_STATS_BLOCKS, 256, 0, st>>>(h->P, h->d_partial, clear);
     k_stats_final<<<1, 256, 0, st>>>(h->d_partial, PTG_STATS_BLOCKS, h->total_steps, stats_dev);
     h->launches += 2;
     if (clear) h->total_steps = 0.0;
+    PTG_CUDA(cudaGetLastError());
+    return PTG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the path's only collective: all-gather + fixed-order combine of the 64-byte statistics record over NCCL
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+// The few NCCL entry points this library needs, resolved at run time from the libnccl.so.2 that is already in the
+// process (torch's wheel ships one) or on the loader path: no link-time dependency, never two NCCLs in one process.
+struct NcclUniqueId { char internal[PTG_NCCL_UNIQUE_ID_BYTES]; };
+struct NcclApi {
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*CommCount)(void*, int*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int /*ncclDataType_t*/, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+const int kNcclFloat64 = 8;     // ncclDataType_t::ncclFloat64 / ncclDouble (nccl.h; stable since NCCL 2.0)
+
+NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) { a.why = std::string("dlopen(libnccl.so.2): ") + dlerror(); return a; }
+        auto sym = [&](const char* name) -> void* {
+            void* p = dlsym(lib, name);
+            if (!p && a.why.empty()) a.why = std::string("libnccl: missing symbol ") + name;
+            return p;
+        };
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+        a.CommCount = reinterpret_cast<decltype(a.CommCount)>(sym("ncclCommCount"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+        a.ok = a.why.empty();
+        return a;
+    }();
+    return api;
+}
+
+int nccl_fail(const char* what, int rc) {
+    NcclApi& a = nccl_api();
+    return fail(PTG_ERR_NCCL, std::string(what) + ": " + (a.GetErrorString ? a.GetErrorString(rc) : "NCCL error"));
+}
+
+__global__ void k_stats_allcombine(const PtgEpisodeStats* gathered, int n_ranks, PtgEpisodeStats* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    PtgEpisodeStats a{};
+    a.min_return = INFINITY; a.max_return = -INFINITY;
+    for (int r = 0; r < n_ranks; ++r) {           // fixed rank order: the same bits on every rank
+        const PtgEpisodeStats s = gathered[r];
+        a.count += s.count; a.sum_return += s.sum_return; a.sum_return_sq += s.sum_return_sq;
+        a.sum_length += s.sum_length; a.total_steps += s.total_steps;
+        a.min_return = fmin(a.min_return, s.min_return); a.max_return = fmax(a.max_return, s.max_return);
+    }
+    *out = a;
+}
+
+}  // namespace
+
+extern "C" int ptg_nccl_unique_id(char id_out[PTG_NCCL_UNIQUE_ID_BYTES]) {
+    if (!id_out) return fail(PTG_ERR_INVALID_ARGUMENT, "null id buffer");
+    NcclApi& a = nccl_api();
+    if (!a.ok) return fail(PTG_ERR_NCCL, a.why);
+    NcclUniqueId id;
+    int rc = a.GetUniqueId(&id);
+    if (rc != 0) return nccl_fail("ncclGetUniqueId", rc);
+    std::memcpy(id_out, id.internal, PTG_NCCL_UNIQUE_ID_BYTES);
+    return PTG_OK;
+}
+
+extern "C" int ptg_nccl_comm_create(const char id[PTG_NCCL_UNIQUE_ID_BYTES], int n_ranks, int rank, void** comm_out) {
+    if (!id || !comm_out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(PTG_ERR_INVALID_ARGUMENT, "bad communicator arguments");
+    NcclApi& a = nccl_api();
+    if (!a.ok) return fail(PTG_ERR_NCCL, a.why);
+    NcclUniqueId uid;
+    std::memcpy(uid.internal, id, PTG_NCCL_UNIQUE_ID_BYTES);
+    void* comm = nullptr;
+    int rc = a.CommInitRank(&comm, n_ranks, uid, rank);
+    if (rc != 0) return nccl_fail("ncclCommInitRank", rc);
+    *comm_out = comm;
+    return PTG_OK;
+}
+
+extern "C" int ptg_nccl_comm_destroy(void* comm) {
+    if (!comm) return PTG_OK;
+    NcclApi& a = nccl_api();
+    if (!a.ok) return fail(PTG_ERR_NCCL, a.why);
+    int rc = a.CommDestroy(comm);
+    return rc == 0 ? PTG_OK : nccl_fail("ncclCommDestroy", rc);
+}
+
+extern "C" int ptg_allreduce_stats(PtgHandle* h, void* nccl_comm, PtgEpisodeStats* stats_dev, void* stream) {
+    if (!h || !nccl_comm || !stats_dev) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle/communicator/stats");
+    int rc = check_device(h, "ptg_allreduce_stats");
+    if (rc != PTG_OK) return rc;
+    NcclApi& a = nccl_api();
+    if (!a.ok) return fail(PTG_ERR_NCCL, a.why);
+    int n_ranks = 0;
+    if ((rc = a.CommCount(nccl_comm, &n_ranks)) != 0) return nccl_fail("ncclCommCount", rc);
+    if (n_ranks > h->gather_ranks) {              // (grown once; earlier buffers stay owned by the handle)
+        PTG_CUDA(h->alloc(&h->d_gather, (size_t)n_ranks));
+        h->gather_ranks = n_ranks;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = a.AllGather(stats_dev, h->d_gather, sizeof(PtgEpisodeStats) / sizeof(double), kNcclFloat64, nccl_comm, st)) != 0)
+        return nccl_fail("ncclAllGather", rc);
+    k_stats_allcombine<<<1, 32, 0, st>>>(h->d_gather, n_ranks, stats_dev);
+    h->launches += 1;
     PTG_CUDA(cudaGetLastError());
     return PTG_OK;
 }
@@ -601,6 +755,7 @@ extern "C" int ptg_vecnorm_moments(PtgHandle* h, const float* reward, double* re
     if (!h || !reward || !returns || !st_in || !moments_out) return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
     if (((uintptr_t)reward & 7) || ((uintptr_t)returns & 15))
         return fail(PTG_ERR_INVALID_ARGUMENT, "reward must be 8-byte and returns 16-byte aligned");
+    if (int rc_dev = check_device(h, "ptg_vecnorm_moments")) return rc_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned grid = (unsigned)std::min<int64_t>(PTG_STATS_BLOCKS, (h->P.n_envs + 511) / 512);
     k_vecnorm_returns<<<grid, 256, 0, st>>>(h->P.n_envs, reward, returns, gamma, st_in, h->d_vn_partial, h->d_vn_ticket,
@@ -617,6 +772,7 @@ extern "C" int ptg_vecnorm_apply(PtgHandle* h, const float* reward_in, const uin
         return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
     if (st_in == st_out) return fail(PTG_ERR_INVALID_ARGUMENT, "st_in and st_out must be distinct buffers");
     if (training && (!moments || n_batch < 1)) return fail(PTG_ERR_INVALID_ARGUMENT, "training needs batch moments");
+    if (int rc_dev = check_device(h, "ptg_vecnorm_apply")) return rc_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned grid = (unsigned)std::min<int64_t>(4 * PTG_STATS_BLOCKS, blocks_for(h->P.n_envs, 256));
     k_vecnorm_apply<<<grid, 256, 0, st>>>(h->P.n_envs, reward_in, done, returns, st_in, st_out,
@@ -635,6 +791,7 @@ extern "C" int ptg_features_dim(const PtgHandle* h) {
 extern "C" int ptg_features(PtgHandle* h, const float* obs, float* feat, void* stream) {
     if (!h || !obs || !feat) return fail(PTG_ERR_INVALID_ARGUMENT, "null argument");
     if (h->P.flat) return fail(PTG_ERR_INVALID_ARGUMENT, "the env already writes flat feature rows (obs_layout = flat)");
+    if (int rc_dev = check_device(h, "ptg_features")) return rc_dev;
     const int F = ptg_features_dim(h);
     k_features<<<blocks_for(h->P.n_envs, PTG_BLOCK), PTG_BLOCK, (size_t)(PTG_BLOCK * F) * sizeof(float),
                  static_cast<cudaStream_t>(stream)>>>(h->P, obs, feat, F);
@@ -693,6 +850,8 @@ extern "C" int ptg_poll_error(PtgHandle* h, void* stream) {
     if (e & PTG_EBIT_ACTION) return fail(PTG_ERR_INVALID_ACTION, "invalid action - must be one of 0..4 [standby, cooldown, startup, partial_load, full_load]");
     if (e & PTG_EBIT_RANGE) return fail(PTG_ERR_DATA_RANGE, "episode clock ran past the end of the market tables (the reference raises IndexError)");
     if (e & PTG_EBIT_TAPE) return fail(PTG_ERR_NOISE_TAPE, "noise tape exhausted");
+    if (e & PTG_EBIT_BOUNDS)
+        return fail(PTG_ERR_DATA_RANGE, "PTG_DEBUG_BOUNDS: a table index left its table (site mask " + std::to_string(e >> 16) + ")");
     return fail(PTG_ERR_INVALID_ARGUMENT, "unknown device error bit");
 }
 
@@ -717,6 +876,8 @@ extern "C" int64_t ptg_bytes_per_env_step(const PtgHandle* h, int action_dtype) 
     const int64_t obs_floats = h->P.flat ? ptg_features_dim(h) : h->P.obs_dim;
     return act + state_rd + state_wr + 4 * obs_floats + 4 + 1;
 }
+
+extern "C" uint32_t ptg_last_step_serial(const PtgHandle* h) { return h ? h->step_serial : 0u; }
 
 extern "C" int ptg_kernel_launches(const PtgHandle* h, int64_t* out) {
     if (!h || !out) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle/out");

@@ -108,16 +108,17 @@ struct RewardConsts {
     int32_t b_s3, _pad;
 };
 
-// --- per-env noise generator: sector 0 of a 64 B line holds everything a draw needs (one 256-bit load, one 128-bit
-//     store); the 64-bit draw counter lives in the cold sector 1 and is only touched when the 12-bit per-env counter
-//     that rides in the spare bits of `tinfo` (already streamed every step) overflows ---
-struct __align__(16) RngRec {
+// --- per-env noise generator: ONE 32 B sector holds everything a draw needs (one 256-bit load, one 128-bit store).
+//     The record is deliberately exactly one sector: 1 M envs are 32 MB, which -- accessed with the evict_last policy
+//     while everything that streams carries evict_first -- stays resident in the 126 MB L2 from step to step, so a
+//     draw is an L2 hit instead of a dependent DRAM round trip.  The cold 64-bit draw counter lives in its own array
+//     (DevParams.draws_total) and is only touched when the 12-bit per-env counter that rides in the spare bits of
+//     `tinfo` (already streamed every step) overflows ---
+struct __align__(32) RngRec {
     uint64_t s_hi, s_lo;   // PCG64 state
     uint64_t i_hi, i_lo;   // PCG64 increment (constant per seed)
-    int64_t draws_total;   // draws folded in from the tinfo counter so far (tape position = draws_total + counter)
-    uint64_t _pad0, _pad1, _pad2;
 };
-static_assert(sizeof(RngRec) == 64, "RngRec layout");
+static_assert(sizeof(RngRec) == 32, "RngRec layout");
 
 #if defined(__CUDACC__)
 // --- 256-bit global accesses (sm_100+: LDG.E.256 / STG.E.256): one instruction and ONE L1 wavefront per lane for a
@@ -166,6 +167,56 @@ __device__ __forceinline__ U256 ld256(const void* p) {          // read-write da
     return r;
 }
 // (256-bit STORES are deliberately not used: ptxas 12.9 turned `st.global.v4.u64` into a single STG.E.64 here.)
+
+// --- L2-resident read-write data (RNG records; per-env plant state when PTG_STATE_L2): evict_last on both sides ---
+__device__ __forceinline__ U256 ld256_keep(const void* p) {
+    U256 r;
+#if PTG_L2_HINTS
+    asm volatile("ld.global.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p), "l"(PTG_L2_EVICT_LAST) : "memory");
+#else
+    r = ld256(p);
+#endif
+    return r;
+}
+__device__ __forceinline__ void st128_keep(void* p, unsigned long long a, unsigned long long b) {
+#if PTG_L2_HINTS
+    asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1,%2}, %3;" ::"l"(p), "l"(a), "l"(b), "l"(PTG_L2_EVICT_LAST) : "memory");
+#else
+    *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(a, b);
+#endif
+}
+__device__ __forceinline__ int4 ld_keep(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(PTG_L2_EVICT_LAST) : "memory");
+    return r;
+}
+__device__ __forceinline__ int2 ld_keep(const int2* p) {
+    int2 r;
+    asm volatile("ld.global.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(PTG_L2_EVICT_LAST) : "memory");
+    return r;
+}
+__device__ __forceinline__ int ld_keep(const int* p) {
+    int r;
+    asm volatile("ld.global.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(PTG_L2_EVICT_LAST) : "memory");
+    return r;
+}
+__device__ __forceinline__ double ld_keep(const double* p) {
+    double r;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(PTG_L2_EVICT_LAST) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_keep(int4* p, int4 v) {
+    asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(PTG_L2_EVICT_LAST) : "memory");
+}
+__device__ __forceinline__ void st_keep(int* p, int v) {
+    asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(PTG_L2_EVICT_LAST) : "memory");
+}
+__device__ __forceinline__ void st_keep(double* p, double v) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(PTG_L2_EVICT_LAST) : "memory");
+}
 #endif
 
 // --- everything a kernel needs, passed by value (__grid_constant__) ---------------------------------------------
@@ -183,6 +234,7 @@ struct DevParams {
     int32_t flat;              // 1 = flat feature-row observation layout (PTG_OBS_FLAT)
     int32_t continuous, eval_mode, noise_mode, schedule_mode;
     int32_t has_penalty;
+    int32_t auto_reset;            // 1: SB3 VecEnv auto-reset inside step | 0: the env stays terminal until ptg_reset
     int32_t prefetch_distance;     // envs between a CTA and the CTA whose state it prefetches into L2
     int32_t action_bytes;          // element size of the action tensor of the current launch
     // tables (device)
@@ -224,7 +276,9 @@ struct DevParams {
     int32_t* ep_count;             // constructor/resets consumed (m)
     int32_t* ep_start;             // SUBPROC schedule: start offset
     uint32_t* nchg;                // state changes this episode (only maintained when has_penalty)
-    RngRec* rng;                   // per-env generator record (one 64 B line)
+    RngRec* rng;                   // per-env generator record (one 32 B sector, L2-resident)
+    int64_t* draws_total;          // draws folded in from the tinfo counter so far (tape position = this + counter); cold
+    uint32_t step_serial;          // serial number of the current ptg_step launch (PtgIO.windows_changed stamp)
     const double* tape;            // tape-mode noise [n_envs][tape_len]
     int64_t tape_len;
     // finished-episode accumulators
@@ -237,6 +291,22 @@ struct DevParams {
 #define PTG_EBIT_RANGE 2u
 #define PTG_EBIT_TAPE 4u
 #define PTG_EBIT_PARTFULL 8u
+#define PTG_EBIT_BOUNDS 16u     // PTG_DEBUG_BOUNDS builds: a table index left its table (site id in the high half)
+
+// -DPTG_DEBUG_BOUNDS: every table index of the hot path is checked against its table; a violation sets the sticky
+// error word (PTG_EBIT_BOUNDS | site << 16), clamps the index and is reported by ptg_poll_error.  The stand-in for
+// compute-sanitizer (closed on the GPU pool): the GPU suite runs once against this build (tools/debug_bounds.sh).
+#ifdef PTG_DEBUG_BOUNDS
+#define PTG_CHECK_INDEX(P, idx, n, site)                                                        \
+    do {                                                                                        \
+        if ((long long)(idx) < 0 || (long long)(idx) >= (long long)(n)) {                       \
+            atomicOr((P).err, PTG_EBIT_BOUNDS | ((uint32_t)(site) << 16));                      \
+            (idx) = (idx) < 0 ? 0 : (n) - 1;                                                    \
+        }                                                                                       \
+    } while (0)
+#else
+#define PTG_CHECK_INDEX(P, idx, n, site) do { } while (0)
+#endif
 
 // What one step produces besides the new state (all in registers).
 struct StepOut {
@@ -261,7 +331,7 @@ struct RngLoad {
 };
 __device__ __forceinline__ RngLoad request_rng(const DevParams& P, int64_t e) {
     RngLoad r;
-    r.lo = ld256(P.rng + e);
+    r.lo = ld256_keep(P.rng + e);
     return r;
 }
 
@@ -273,7 +343,7 @@ __device__ __forceinline__ double draw_noise(const DevParams& P, int64_t e, cons
     RngRec* rec = P.rng + e;
     double out;
     if (P.noise_mode == PTG_NOISE_TAPE) {
-        const int64_t d = rec->draws_total + (int64_t)draws_ep;
+        const int64_t d = P.draws_total[e] + (int64_t)draws_ep;
         if (d >= P.tape_len) { atomicOr(P.err, PTG_EBIT_TAPE); out = 0.0; }
         else out = P.tape[e * P.tape_len + d];
     } else {
@@ -281,11 +351,11 @@ __device__ __forceinline__ double draw_noise(const DevParams& P, int64_t e, cons
         ZigTables zt = P.zig;
         zt.kiwi = zig_kiwi;         // the CTA's shared-memory copy of the hot {ki, wi} pairs
         const double z = pcg64_standard_normal(g, zt);
-        reinterpret_cast<ulonglong2*>(rec)[0] = make_ulonglong2(g.s_hi, g.s_lo);
+        st128_keep(rec, g.s_hi, g.s_lo);
         out = 0.0 + P.noise * z;    // random_normal: loc + scale * standard_normal
     }
     if (++draws_ep == PTG_TI_DRAW_MAX) {            // rare: fold the small counter into the 64-bit one
-        rec->draws_total += (int64_t)PTG_TI_DRAW_MAX;
+        P.draws_total[e] += (int64_t)PTG_TI_DRAW_MAX;
         draws_ep = 0;
     }
     return out;
@@ -352,6 +422,7 @@ __device__ __forceinline__ void episode_offsets(const DevParams& P, int64_t e, i
     int64_t gid = P.env_id_offset + e, slot;
     if (P.schedule_mode == PTG_SCHED_DUMMY) slot = (P.n_envs_global * (int64_t)m + gid) % P.n_eps_ind;
     else slot = ((int64_t)P.ep_start[e] + m) % P.n_eps_ind;
+    PTG_CHECK_INDEX(P, slot, (int64_t)P.n_eps_ind, 7);
     double v = (double)P.eps_ind[slot];
     ep_h = (int)(v * P.eps_len_d * 24);           // :60 / :491
     ep_d = (int)(v * P.eps_len_d);                // :61 / :492
@@ -430,7 +501,11 @@ __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, c
         if (to_partial) chain = src == PTG_DS_OP2_START_F ? PTG_CHAIN_P_FROM_OP2F : src == PTG_DS_OP3_P_F ? PTG_CHAIN_P_FROM_OP3 : -1;
         else chain = src == PTG_DS_OP1_START_P ? PTG_CHAIN_F_FROM_OP1 : src == PTG_DS_OP8_F_P ? PTG_CHAIN_F_FROM_OP8 : -1;
         uint32_t c = chain_pack(to_partial ? PTG_DS_OP8_F_P : PTG_DS_OP3_P_F, PTG_CHAIN_J_ONE, 0);   // :684-688, :750-754
-        if (chain >= 0) c = __ldg(P.chain_tab + chain * (P.chain_top + 1) + min(i + j * S, P.chain_top));
+        if (chain >= 0) {
+            int t_op = min(i + j * S, P.chain_top);
+            PTG_CHECK_INDEX(P, t_op, P.chain_top + 1, 3);
+            c = __ldg(P.chain_tab + chain * (P.chain_top + 1) + t_op);
+        }
         ds = c >> 27;
         const uint32_t rule = (c >> 25) & 3u;
         const int new_i = (int)(c & 0x1ffffffu);
@@ -441,6 +516,7 @@ __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, c
     }
     // _perform_sim_step (:525-557) reduced to index arithmetic: the window [pos-S, pos) clipped/padded at L is
     // entry min(pos - S, L) of table ds (built by k_build_step_tab with the same padding / hand-over rules)
+    PTG_CHECK_INDEX(P, ds, PTG_N_DATASETS, 1);
     const int L = P.ds_len[ds];
     const long long pos = (long long)i + (long long)j * S;
     long long start = pos - S;
@@ -453,6 +529,7 @@ __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, c
         }
     }
     meta = (meta & ~7u) | (uint32_t)state;
+    PTG_CHECK_INDEX(P, start, (long long)L + 1, 2);
     return P.ent_off[ds] + (int)start;
 }
 

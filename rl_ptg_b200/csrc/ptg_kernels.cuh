@@ -529,8 +529,9 @@ __global__ void k_construct(const __grid_constant__ DevParams P) {
     // SeedSequence(global id) so that an unseeded run is still reproducible.
     Pcg64 g = pcg64_from_seed((uint64_t)gid);
     RngRec rr = {};
-    rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo; rr.draws_total = 0;
+    rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo;
     P.rng[e] = rr;
+    P.draws_total[e] = 0;
     if (P.schedule_mode == PTG_SCHED_SUBPROC) {
         // :43-44 draws ep_index = integers(0, n_eps_loops) from an UNSEEDED generator per worker process (not
         // reproducible in the reference); here: a fixed stream per global env id, same range
@@ -574,8 +575,9 @@ __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ Dev
         if (seeds != nullptr && seeds[e] >= 0) {          // gymnasium Env.reset(seed=...): a fresh generator
             Pcg64 g = pcg64_from_seed((uint64_t)seeds[e]);
             RngRec rr = {};
-            rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo; rr.draws_total = 0;
+            rr.s_hi = g.s_hi; rr.s_lo = g.s_lo; rr.i_hi = g.i_hi; rr.i_lo = g.i_lo;
             P.rng[e] = rr;
+            P.draws_total[e] = 0;
             tinfo = 0;
         }
         m = meta_unpack((uint32_t)P.core[e].w);
@@ -626,6 +628,7 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
     P.fin_len_sum[e] += (double)k;
     P.fin_min[e] = fmin(P.fin_min[e], ep_ret);
     P.fin_max[e] = fmax(P.fin_max[e], ep_ret);
+    if (!P.auto_reset) return;           // Gymnasium single-env semantics: the caller resets (PtgConfig.auto_reset = 0)
     const int32_t mc = P.ep_count[e] + 1;
     P.ep_count[e] = mc;
     Meta m;
@@ -643,14 +646,32 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
 #define PTG_STEP_MIN_BLOCKS 4        // CTAs of 256 threads per SM the step kernel is compiled for (<= 64 registers)
 #endif
 
+// Per-env plant state (core, tinfo, ep, ep_ret: 36 B read + 28 B written per env-step).  PTG_STATE_L2 = 1 keeps it in
+// L2 between steps (evict_last on loads and stores; 36 MB at 1 M envs next to 32 MB of RNG records and 16 MB of tables
+// in the 126 MB L2, while observations / rewards / actions stream with evict_first); 0 = streamed (round-1 behaviour).
+#ifndef PTG_STATE_L2
+#define PTG_STATE_L2 1
+#endif
+#ifndef PTG_PREFETCH_STATE
+#define PTG_PREFETCH_STATE 1     // prefetch.global.L2 of the plant state of the CTA one scheduling wave later
+#endif
+#if PTG_STATE_L2 && PTG_L2_HINTS
+#define PTG_LD_STATE(p) ld_keep(p)
+#define PTG_ST_STATE(p, v) st_keep(p, v)
+#else
+#define PTG_LD_STATE(p) (*(p))
+#define PTG_ST_STATE(p, v) st_stream(p, v)
+#endif
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ long long load_action_raw(const void* __restrict__ actions, int adtype, int64_t idx) {
-    if (adtype == PTG_ACT_I64) return __ldg((const long long*)actions + idx);
-    if (adtype == PTG_ACT_I32) return __ldg((const int*)actions + idx);
-    if (adtype == PTG_ACT_U8) return __ldg((const unsigned char*)actions + idx);
-    return (long long)__float_as_int(__ldg((const float*)actions + idx));      // F32: raw bits
+    // streamed once per step (ld.global.cs: evict-first), so the action tensor does not displace L2-resident state
+    if (adtype == PTG_ACT_I64) return __ldcs((const long long*)actions + idx);
+    if (adtype == PTG_ACT_I32) return __ldcs((const int*)actions + idx);
+    if (adtype == PTG_ACT_U8) return __ldcs((const unsigned char*)actions + idx);
+    return (long long)__float_as_int(__ldcs((const float*)actions + idx));      // F32: raw bits
 }
 
 // Decode the action of an env (discrete id, or continuous Box(-1,1) -> 5 bins, :346-355) from load_action_raw.
@@ -718,7 +739,11 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         const Plan plan = plan_transition(action, meta, tinfo & 7);
         uint32_t draws_ep = ti_draws(tinfo);
         int lut_val = 0;
-        if (plan.col >= 0) lut_val = ldg32_nc_keep(P.argmin_lut + ti_id(tinfo) * PTG_N_ARGMIN + plan.col);
+        if (plan.col >= 0) {
+            int vid = ti_id(tinfo);
+            PTG_CHECK_INDEX(P, vid, P.n_vals, 4);
+            lut_val = ldg32_nc_keep(P.argmin_lut + vid * PTG_N_ARGMIN + plan.col);
+        }
         const bool draws = plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF;
         if (draws) prefetch_l1(P.rng + e);
         // (2) clock of step k+1 (:442-445, integer form of floor(clock_hours), floor(clock_days)) -> market rows of
@@ -730,7 +755,9 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         clamp_market_index(P, t_hour, t_day);
         load_hour_row<NV>(P, t_hour, hrow);
         day = load_day_row(P, t_day);
-        const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + (k + 1)));
+        int k1 = k + 1;
+        PTG_CHECK_INDEX(P, k1, P.eps_sim_steps + 1, 5);
+        const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
         stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
         const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
         // the window tiles go to the TMA before the transition: the fence in front of a bulk store waits for the
@@ -760,9 +787,9 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
             write_info<NV>(P, io.info, e, InfoKey{k, t_hour, t_day, ent, state_change, meta, rew,
                                                   ep_ret + (double)nchg * P.penalty});
         k += 1;
-        if (done) {                                   // SB3 auto-reset (DummyVecEnv.step_wait), out of line
-            finish_episode<NV, MOD>(P, io, e, single, k, ep_ret, (meta >> 4) & 7, ObsKey{ent, t_hour, t_day, (int)(meta & 7), k},
-                                    draws_ep);
+        if (done) finish_episode<NV, MOD>(P, io, e, single, k, ep_ret, (meta >> 4) & 7,
+                                          ObsKey{ent, t_hour, t_day, (int)(meta & 7), k}, draws_ep);
+        if (done && P.auto_reset) {                   // SB3 auto-reset (DummyVecEnv.step_wait), out of line
             const int4 core = P.core[e];              // the reset state written by finish_episode
             tinfo = P.tinfo[e]; ep = P.ep[e];
             i = core.x; j = core.y; k = core.z; meta = (uint32_t)core.w; ep_ret = 0.0;
@@ -799,7 +826,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         st_stream(done_out + e, (uint8_t)done);
     }
     if (single && io.windows_changed != nullptr && __any_sync(0xffffffffu, win_moved) && lane == 0)
-        *io.windows_changed = 1u;                   // (same value from every warp: plain store, no atomic needed)
+        *io.windows_changed = P.step_serial;        // (same value from every warp: plain store, no atomic needed)
 }
 
 // One env step with the flat observation layout: the same transition / reward path as step_one, but the whole
@@ -826,14 +853,20 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
         const Plan plan = plan_transition(action, meta, tinfo & 7);
         uint32_t draws_ep = ti_draws(tinfo);
         int lut_val = 0;
-        if (plan.col >= 0) lut_val = ldg32_nc_keep(P.argmin_lut + ti_id(tinfo) * PTG_N_ARGMIN + plan.col);
+        if (plan.col >= 0) {
+            int vid = ti_id(tinfo);
+            PTG_CHECK_INDEX(P, vid, P.n_vals, 4);
+            lut_val = ldg32_nc_keep(P.argmin_lut + vid * PTG_N_ARGMIN + plan.col);
+        }
         if (plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF) prefetch_l1(P.rng + e);
         const unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
         int t_hour = ep.x + (int)(sec / 3600u), t_day = ep.y + (int)(sec / 86400u);
         clamp_market_index(P, t_hour, t_day);
         load_hour_row<4>(P, t_hour, hrow);
         day = load_day_row(P, t_day);
-        const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + (k + 1)));
+        int k1 = k + 1;
+        PTG_CHECK_INDEX(P, k1, P.eps_sim_steps + 1, 5);
+        const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
         stage_flat_early<MOD>(row, hrow, day, pf0, pr12);
         const double el = hour_row_el<4>(hrow);
         const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep);
@@ -854,9 +887,9 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
         o.sin_h = sc2.x; o.cos_h = sc2.y;
         if (P.has_penalty) P.nchg[e] += (uint32_t)state_change;
         k += 1;
-        if (done) {                                   // SB3 auto-reset: the returned row is the reset observation
-            finish_episode<4, MOD, true>(P, io, e, single, k, ep_ret, (meta >> 4) & 7,
-                                         ObsKey{ent, t_hour, t_day, (int)(meta & 7), k}, draws_ep);
+        if (done) finish_episode<4, MOD, true>(P, io, e, single, k, ep_ret, (meta >> 4) & 7,
+                                               ObsKey{ent, t_hour, t_day, (int)(meta & 7), k}, draws_ep);
+        if (done && P.auto_reset) {                   // SB3 auto-reset: the returned row is the reset observation
             const int4 core = P.core[e];
             tinfo = P.tinfo[e]; ep = P.ep[e];
             i = core.x; j = core.y; k = core.z; meta = (uint32_t)core.w; ep_ret = 0.0;
@@ -931,15 +964,16 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     const bool active = e < n_envs;
     const int le = active ? e : n_envs - 1;             // tail lanes shadow the last env (no stores)
 
-    const int4 core = P.core[le];
-    int32_t tinfo = P.tinfo[le];
-    int2 ep = P.ep[le];
-    double ep_ret = P.ep_ret[le];
+    const int4 core = PTG_LD_STATE(P.core + le);
+    int32_t tinfo = PTG_LD_STATE(P.tinfo + le);
+    int2 ep = PTG_LD_STATE(P.ep + le);
+    double ep_ret = PTG_LD_STATE(P.ep_ret + le);
     long long action_raw = load_action_raw(actions, adtype, le);
     if (!PERSIST && use_zig) __syncthreads();           // (one tile per CTA: the barrier sits behind the state loads)
     if (!warp_in_range) continue;                       // whole warp out of range
     int i = core.x, j = core.y, k = core.z;
     uint32_t meta = (uint32_t)core.w;
+#if PTG_PREFETCH_STATE
     {   // pull the plant state of the CTA that will run one scheduling wave later into L2 (fire and forget)
         const int pe = e + P.prefetch_distance;
         if (pe < n_envs) {
@@ -950,6 +984,7 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
             if (!MANY && (lane & 3) == 3) prefetch_l2(reinterpret_cast<const char*>(actions) + (int64_t)pe * P.action_bytes);
         }
     }
+#endif
 
     const uint64_t* zig = use_zig ? zig_kiwi : nullptr;
     if (!MANY) {
@@ -971,9 +1006,9 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
         }
     }
     if (active) {
-        st_stream(P.core + e, make_int4(i, j, k, (int)meta));
-        st_stream(P.tinfo + e, tinfo);
-        st_stream(P.ep_ret + e, ep_ret);
+        PTG_ST_STATE(P.core + e, make_int4(i, j, k, (int)meta));
+        PTG_ST_STATE(P.tinfo + e, tinfo);
+        PTG_ST_STATE(P.ep_ret + e, ep_ret);
     }
     }
     if (lane == 0) tma_store_wait_read();               // the staging buffer must outlive the bulk stores' reads
@@ -1048,6 +1083,8 @@ struct StateDev {
             *act_ep_h, *act_ep_d, *episode_count;
     int64_t* draws;
     double *t_cat, *cum_reward;
+    uint64_t* rng;            // [n][4] = {state_hi, state_lo, inc_hi, inc_lo}
+    uint32_t* state_changes;
 };
 
 __global__ void k_state_unpack(const __grid_constant__ DevParams P, StateDev s, const double* vals) {
@@ -1061,7 +1098,10 @@ __global__ void k_state_unpack(const __grid_constant__ DevParams P, StateDev s, 
     s.partial_ds[e] = m.part_ds; s.full_ds[e] = m.full_ds; s.current_action[e] = m.cur_action;
     const int2 ep = P.ep[e];
     s.act_ep_h[e] = ep.x; s.act_ep_d[e] = ep.y; s.episode_count[e] = P.ep_count[e];
-    s.draws[e] = P.rng[e].draws_total + (int64_t)ti_draws(P.tinfo[e]);
+    s.draws[e] = P.draws_total[e] + (int64_t)ti_draws(P.tinfo[e]);
+    const RngRec rr = P.rng[e];
+    s.rng[4 * e] = rr.s_hi; s.rng[4 * e + 1] = rr.s_lo; s.rng[4 * e + 2] = rr.i_hi; s.rng[4 * e + 3] = rr.i_lo;
+    s.state_changes[e] = P.has_penalty ? P.nchg[e] : 0u;
     s.t_cat[e] = vals[ti_id(P.tinfo[e])];
     s.cum_reward[e] = P.ep_ret[e];
 }
@@ -1076,7 +1116,11 @@ __global__ void k_state_pack(const __grid_constant__ DevParams P, StateDev s, co
     P.core[e] = make_int4(s.i[e], s.j[e], s.k[e], (int)meta_pack(m));
     P.ep[e] = make_int2(s.act_ep_h[e], s.act_ep_d[e]);
     P.ep_count[e] = s.episode_count[e];
-    P.rng[e].draws_total = s.draws[e];            // (the 12-bit counter in tinfo restarts at 0 below)
+    P.draws_total[e] = s.draws[e];                // (the 12-bit counter in tinfo restarts at 0 below)
+    RngRec rr;
+    rr.s_hi = s.rng[4 * e]; rr.s_lo = s.rng[4 * e + 1]; rr.i_hi = s.rng[4 * e + 2]; rr.i_lo = s.rng[4 * e + 3];
+    P.rng[e] = rr;
+    if (P.has_penalty) P.nchg[e] = s.state_changes[e];
     P.tinfo[e] = tinfo_of(B, s.t_cat[e]);        // t_cat must be a temperature present in the tables (or 16)
     P.ep_ret[e] = s.cum_reward[e];
 }

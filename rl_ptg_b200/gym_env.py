@@ -5,9 +5,11 @@ Same constructor (``dict_input, train_or_eval="train", render_mode="None"``), ``
 (obs, info)`` and ``step(action) -> (obs, reward, terminated, truncated, info)`` as the reference class, same
 ``observation_space`` / ``action_space``.  It is a batch of ONE env: every call is a kernel launch plus a device
 synchronisation (tens of microseconds), so it exists for API completeness, spot checks and ``gym.make``-style
-callers -- throughput comes from ``PtGVecEnv``.  Unlike the ``VecEnv`` it does NOT auto-reset: after ``terminated``
-the caller resets, as with any Gymnasium env (the reference's process-global episode counter becomes this object's
-own reset count, so it walks ``eps_ind`` like a lone reference env does).
+callers -- throughput comes from ``PtGVecEnv``.  Unlike the ``VecEnv`` it does NOT auto-reset
+(``PtgConfig.no_auto_reset``): the step that terminates returns the terminal observation and leaves the env as it
+is; only ``reset()`` consumes the next ``eps_ind`` entry.  A lone env therefore walks ``eps_ind[0]`` (constructor),
+``[1]``, ``[2]``, ... exactly like a lone reference env (``env/ptg_gym_env.py:59-62, 490-493``; pinned by the
+train-mode golden case ``single_env_train_resets``).
 """
 from __future__ import annotations
 
@@ -22,7 +24,8 @@ class PTGEnv:
     def __init__(self, dict_input: dict, train_or_eval: str = "train", render_mode: str = "None",
                  device="cuda:0", noise: str = "numpy"):
         # eval-mode kernel variant: the info block is written every step; train mode returns {} like the reference
-        self._venv = PtGVecEnv(dict_input, 1, train_or_eval="eval", render_mode=render_mode, device=device, noise=noise)
+        self._venv = PtGVecEnv(dict_input, 1, train_or_eval="eval", render_mode=render_mode, device=device, noise=noise,
+                               auto_reset=False)
         self.train_or_eval = train_or_eval
         self.render_mode = render_mode
         self.observation_space = self._venv.observation_space
@@ -50,13 +53,11 @@ class PTGEnv:
         obs, rew, done, infos = self._venv.step(a)
         info = dict(infos[0])
         terminated = bool(done[0])
-        if terminated:                               # undo the VecEnv's auto-reset view: hand out the last obs
-            obs_single = {k: (int(v) if k == "METH_STATUS" else np.array(v, dtype=np.float64))
-                          for k, v in info.pop("terminal_observation").items()}
-            info.pop("episode", None), info.pop("TimeLimit.truncated", None)
+        if terminated:                               # Monitor / VecEnv annotations are not part of the Gymnasium API
+            for key in ("terminal_observation", "episode", "TimeLimit.truncated"):
+                info.pop(key, None)
             self._terminated = True
-        else:
-            obs_single = self._single(obs)
+        obs_single = self._single(obs)               # (no auto-reset: at `terminated` this IS the terminal observation)
         if self.train_or_eval != "eval":
             info = {}                                # :471-474
         return obs_single, float(rew[0]), terminated, False, info

@@ -36,6 +36,8 @@ except ModuleNotFoundError:
 _NOISE = {"numpy": _abi.NOISE_NUMPY, "tape": _abi.NOISE_TAPE, "off": _abi.NOISE_OFF}
 _TORCH_ACT = {torch.int64: _abi.ACT_I64, torch.int32: _abi.ACT_I32, torch.uint8: _abi.ACT_U8,
               torch.float32: _abi.ACT_F32}
+_TORCH_FROM_NUMPY_OK = (np.dtype(np.int64), np.dtype(np.int32), np.dtype(np.uint8), np.dtype(np.int16),
+                        np.dtype(np.int8), np.dtype(np.float32))
 
 
 def shard_range(n_envs_global: int, rank: int, world_size: int) -> tuple[int, int]:
@@ -115,13 +117,26 @@ class _VecEnvBase:
 _Base = _SB3VecEnv if _SB3VecEnv is not None else _VecEnvBase
 
 
+class StepGraph:
+    """Steps captured by ``PtGVecEnv.capture_steps``: ``replay()`` issues them with one host call.  The replay
+    invalidates the numpy API's host mirror of the market-window blocks (the steps bypass ``step_wait``), so a
+    ``step()`` that follows re-transfers them."""
+
+    def __init__(self, env: "PtGVecEnv", graph: "torch.cuda.CUDAGraph"):
+        self.env, self.graph = env, graph
+
+    def replay(self) -> None:
+        self.env._win_valid = False
+        self.graph.replay()
+
+
 class PtGVecEnv(_Base):
     metadata = {"render_modes": ["None"]}
 
     def __init__(self, dict_input: dict, n_envs: int, train_or_eval: str = "train", render_mode: str = "None",
                  seed: int | None = None, device: str | torch.device = "cuda:0", noise: str = "numpy",
                  env_id_offset: int = 0, n_envs_global: int | None = None, obs_dtype=np.float32,
-                 info_limit: int = 4096, obs_layout: str = "dict"):
+                 info_limit: int = 4096, obs_layout: str = "dict", auto_reset: bool = True):
         if noise not in _NOISE:
             raise ValueError(f"noise must be one of {sorted(_NOISE)}")
         if obs_layout not in ("dict", "flat"):
@@ -138,7 +153,9 @@ class PtGVecEnv(_Base):
         self.n_envs_global = int(n_envs_global if n_envs_global is not None else n_envs)
         self.env_id_offset = int(env_id_offset)
         self.cfg = _abi.config_from_kwargs(dict_input, train_or_eval, _NOISE[noise],
-                                           obs_layout=_abi.OBS_FLAT if obs_layout == "flat" else _abi.OBS_KEY_MAJOR)
+                                           obs_layout=_abi.OBS_FLAT if obs_layout == "flat" else _abi.OBS_KEY_MAJOR,
+                                           auto_reset=auto_reset)
+        self.auto_reset = bool(auto_reset)
         tables, keep = _abi.tables_from_kwargs(dict_input, self.cfg.price_ahead)
         self.raw_modified = dict_input["raw_modified"]
         self.action_type = dict_input["action_type"]
@@ -174,6 +191,7 @@ class PtGVecEnv(_Base):
         self._ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
         self._ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
         self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._win_flag = torch.zeros(1, dtype=torch.int32, device=dev)     # PtgIO.windows_changed (step serial stamp)
         self._obs_dict = self._obs_views(self._obs)          # views are created once; buffers are reused
         self._io = self._make_io(self._obs, self._reward, self._done, self._term_obs,
                                  self._info if self.cfg.train_or_eval else None, self._ep_ret, self._ep_len)
@@ -184,9 +202,9 @@ class PtGVecEnv(_Base):
         self._flip = 0
         # The market-window blocks (3/4 of the observation bytes) only change when an env's clock crosses an hour or
         # its episode ends: the step kernel raises `windows_changed` then, and the host mirror re-transfers those
-        # blocks only on such steps.  They live in whichever of the two host buffers received them last (_win_buf);
+        # blocks only on such steps (the flag then carries the serial number of that step, so it never needs clearing).
+        # They live in whichever of the two host buffers received them last (_win_buf);
         # a new version always goes to the OTHER buffer, so the dict handed out before stays intact.
-        self._win_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._win_flag_h = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._win_buf = 0
         self._win_valid = False                  # host copy of the window blocks matches the device's
@@ -199,8 +217,13 @@ class PtGVecEnv(_Base):
         self._ep_ret_h = torch.zeros(n, dtype=torch.float64).pin_memory()
         self._ep_len_h = torch.zeros(n, dtype=torch.int32).pin_memory()
         act_dtype = torch.float32 if self.action_type == "continuous" else torch.int64
-        self._act_h = torch.zeros(n, dtype=act_dtype).pin_memory()
-        self._act_d = torch.zeros(n, dtype=act_dtype, device=dev)
+        self._act_wire_u8 = self.action_type != "continuous"
+        wire_dtype = torch.uint8 if self._act_wire_u8 else act_dtype
+        self._act_h = torch.zeros(n, dtype=wire_dtype).pin_memory()
+        self._act_d = torch.zeros(n, dtype=wire_dtype, device=dev)
+        self.h2d_bytes_per_step = n * self._act_h.element_size()
+        self._step_serial = 0
+        self._comm = None                        # ncclComm_t of the statistics all-gather (created on first use)
         self._tape = None
         self._t_start = time.time()
         self._ev_small = torch.cuda.Event()
@@ -227,7 +250,7 @@ class PtGVecEnv(_Base):
         io.info = info.data_ptr() if info is not None else None
         io.episode_return = ep_ret.data_ptr() if ep_ret is not None else None
         io.episode_length = ep_len.data_ptr() if ep_len is not None else None
-        io.windows_changed = None
+        io.windows_changed = self._win_flag.data_ptr() if (reward is not None and self.obs_layout != "flat") else None
         return io
 
     def _stream(self):
@@ -316,18 +339,30 @@ class PtGVecEnv(_Base):
         if self.action_type == "continuous":
             a = a.astype(np.float32, copy=False).reshape(self.num_envs)
         else:
-            a = a.astype(np.int64, copy=False).reshape(self.num_envs)
-        if a.flags.c_contiguous and a.flags.writeable:
-            self._act_h.copy_(torch.from_numpy(a))          # torch's copy is multi-threaded for large arrays
+            if a.dtype.kind not in "iu":
+                a = a.astype(np.int64)
+            a = a.reshape(self.num_envs)
+        # Discrete actions travel as uint8 (the ABI takes PTG_ACT_U8): 1 byte per env over PCIe instead of SB3's int64.
+        # Values outside 0..4 map to 255, which the kernel reports like any other invalid action.  torch's converting
+        # copy is multi-threaded for large arrays (torch.set_num_threads; under torchrun OMP_NUM_THREADS defaults to 1).
+        if a.flags.c_contiguous and a.dtype in _TORCH_FROM_NUMPY_OK:
+            src = torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
+            if self._act_wire_u8:
+                if self.num_envs <= 4096:
+                    bad = (a < 0) | (a > 4)
+                    if bad.any():
+                        src = torch.from_numpy(np.where(bad, 255, a))
+                    self._act_h.copy_(src)
+                else:
+                    self._act_h.copy_(src.clamp(-1, 5))         # -1 -> 255, 5 stays invalid
+            else:
+                self._act_h.copy_(src)
         else:
-            self._act_h.numpy()[:] = a
+            self._act_h.numpy()[:] = np.where((a < 0) | (a > 4), 255, a) if self._act_wire_u8 else a
         self._act_d.copy_(self._act_h, non_blocking=True)
-        if self.obs_layout != "flat":
-            self._win_flag.zero_()
-            self._io.windows_changed = self._win_flag.data_ptr()
         _lib.check(self._L.ptg_step(self._h, self._ptr(self._act_d), _TORCH_ACT[self._act_d.dtype],
                                     C.byref(self._io), self._stream()))
-        self._io.windows_changed = None
+        self._step_serial = int(self._L.ptg_last_step_serial(self._h))
 
     def step_wait(self):
         obs_h = self._next_obs_host()
@@ -356,7 +391,7 @@ class PtGVecEnv(_Base):
             self.d2h_bytes += self._info_h.numel() * 8
         self._ev_small.synchronize()
         # window blocks: only when the step moved them (or the host copy is not known to be current)
-        if cut > 0 and (not self._win_valid or int(self._win_flag_h[0]) != 0):
+        if cut > 0 and (not self._win_valid or (int(self._win_flag_h[0]) & 0xffffffff) == self._step_serial):
             # a new version goes to the buffer that does not hold the version handed out last
             self._win_buf = (self._win_buf ^ 1) if self._win_valid else self._flip
             self._obs_hh[self._win_buf][:cut].copy_(self._obs[:cut], non_blocking=True)
@@ -405,6 +440,9 @@ class PtGVecEnv(_Base):
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None:
+            if getattr(self, "_comm", None) is not None:
+                self._L.ptg_nccl_comm_destroy(self._comm)
+                self._comm = None
             self._L.ptg_destroy(self._h)
             self._h = None
 
@@ -519,7 +557,7 @@ class PtGVecEnv(_Base):
         self._win_valid = False
         return out
 
-    def capture_steps(self, action_buffers: Sequence[torch.Tensor]) -> "torch.cuda.CUDAGraph":
+    def capture_steps(self, action_buffers: Sequence[torch.Tensor]) -> "StepGraph":
         """Capture ``len(action_buffers)`` consecutive single steps into ONE CUDA graph (SURVEY.md build plan item 7):
         ``graph.replay()`` then issues them with a single host call -- for shards small enough that a step (a few us)
         costs less than a Python/driver launch.  The steps read ``action_buffers[q]`` (fill them before each
@@ -535,7 +573,7 @@ class PtGVecEnv(_Base):
         with torch.cuda.graph(graph):
             for a in action_buffers:
                 self.step_tensor(a)
-        return graph
+        return StepGraph(self, graph)
 
     def obs_views_of(self, buf: torch.Tensor) -> dict:
         """Key views of any single obs buffer with this env's layout (e.g. ``rollout['obs'][t]``)."""
@@ -567,7 +605,7 @@ class PtGVecEnv(_Base):
         keep = {}
         for name, dt in _abi.STATE_FIELDS:
             keep[name] = np.ascontiguousarray(arrays[name], dtype=dt)
-            assert keep[name].shape == (self.num_envs,)
+            assert keep[name].shape == _abi.state_shape(name, self.num_envs), name
             setattr(s, name, keep[name].ctypes.data)
         _lib.check(self._L.ptg_set_state(self._h, C.byref(s)))
         self._win_valid = False
@@ -577,13 +615,58 @@ class PtGVecEnv(_Base):
         _lib.check(self._L.ptg_kernel_launches(self._h, C.byref(v)))
         return int(v.value)
 
-    def episode_stats(self, clear: bool = True, reduce: bool = True) -> dict:
-        """Finished-episode statistics since the last clear: device reduction (warp shuffles, deterministic),
-        then -- if torch.distributed is initialised and ``reduce`` -- ONE all-gather of the 64-byte record over
-        NCCL/NVLink (gloo on CPU tests) and a fixed-order combine."""
+    def _nccl_comm(self):
+        """ncclComm_t for ``ptg_allreduce_stats``, created once: rank 0's unique id travels over torch.distributed."""
+        import torch.distributed as dist
+        if self._comm is None:
+            world, rank = dist.get_world_size(), dist.get_rank()
+            buf = C.create_string_buffer(_abi.PTG_NCCL_UNIQUE_ID_BYTES)
+            if rank == 0:
+                _lib.check(self._L.ptg_nccl_unique_id(buf))
+            t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(self.device)
+            dist.broadcast(t, 0)
+            ident = bytes(t.cpu().numpy().tobytes())
+            comm = C.c_void_p()
+            with torch.cuda.device(self._dev_index):
+                _lib.check(self._L.ptg_nccl_comm_create(ident, world, rank, C.byref(comm)))
+            self._comm = comm
+        return self._comm
+
+    def episode_stats_async(self, clear: bool = True, reduce: bool = True) -> torch.Tensor:
+        """Device-side part of ``episode_stats``: the reduction over this rank's envs and -- with NCCL initialised --
+        the cross-rank all-gather + combine inside the library (``ptg_allreduce_stats``), all on the current stream
+        without a host synchronisation.  Returns the 8 x fp64 ``PtgEpisodeStats`` record (device tensor, reused)."""
+        import torch.distributed as dist
         self._check_open()
         _lib.check(self._L.ptg_episode_stats(self._h, self._ptr(self._stats), int(clear), self._stream()))
-        return combine_stats(self._stats, reduce)
+        if (reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                and dist.get_backend() == "nccl"):
+            _lib.check(self._L.ptg_allreduce_stats(self._h, self._nccl_comm(), self._ptr(self._stats), self._stream()))
+            self._stats_ranks = dist.get_world_size()
+        else:
+            self._stats_ranks = 1
+        return self._stats
+
+    def episode_stats(self, clear: bool = True, reduce: bool = True) -> dict:
+        """Finished-episode statistics since the last clear: device reduction (warp shuffles, deterministic), then --
+        if torch.distributed is initialised and ``reduce`` -- ONE all-gather of the 64-byte record over NCCL/NVLink
+        inside the library (``ptg_allreduce_stats``; gloo falls back to ``combine_stats``) and a fixed-order combine."""
+        import torch.distributed as dist
+        stats = self.episode_stats_async(clear, reduce)
+        if self._stats_ranks > 1:
+            return stats_dict(stats.cpu().numpy(), self._stats_ranks)
+        return combine_stats(stats, reduce and not (dist.is_available() and dist.is_initialized()
+                                                   and dist.get_backend() == "nccl" and dist.get_world_size() > 1))
+
+
+def stats_dict(rec: np.ndarray, ranks: int) -> dict:
+    """The user-facing view of one (combined) 8 x fp64 ``PtgEpisodeStats`` record."""
+    n, s1, s2, sl, mn, mx, steps = (float(v) for v in rec[:7])
+    mean = s1 / n if n > 0 else float("nan")
+    var = max(s2 / n - mean * mean, 0.0) if n > 0 else float("nan")
+    return {"episodes": int(n), "return_mean": mean, "return_std": var ** 0.5,
+            "length_mean": sl / n if n > 0 else float("nan"), "return_min": mn, "return_max": mx,
+            "env_steps": int(steps), "ranks": int(ranks)}
 
 
 def combine_stats(stats: torch.Tensor, reduce: bool = True) -> dict:
@@ -602,9 +685,5 @@ def combine_stats(stats: torch.Tensor, reduce: bool = True) -> dict:
             setattr(arr[r], name, float(per_rank[r, f]))
     out = _abi.PtgEpisodeStats()
     L.ptg_stats_combine(arr, per_rank.shape[0], C.byref(out))
-    n = out.count
-    mean = out.sum_return / n if n > 0 else float("nan")
-    var = max(out.sum_return_sq / n - mean * mean, 0.0) if n > 0 else float("nan")
-    return {"episodes": int(n), "return_mean": mean, "return_std": var ** 0.5, "length_mean": out.sum_length / n if n > 0
-            else float("nan"), "return_min": out.min_return, "return_max": out.max_return,
-            "env_steps": int(out.total_steps), "ranks": int(per_rank.shape[0])}
+    rec = np.array([getattr(out, name) for name, _ in _abi.PtgEpisodeStats._fields_])
+    return stats_dict(rec, per_rank.shape[0])

@@ -24,14 +24,14 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    # PtgConfig: 35 int32 then 43 doubles, no padding surprises
-    assert C.sizeof(_abi.PtgConfig) == 35 * 4 + 4 + 43 * 8
+    # PtgConfig: 36 int32 then 43 doubles, no padding surprises
+    assert C.sizeof(_abi.PtgConfig) == 36 * 4 + 43 * 8
     assert _abi.PtgConfig.noise.offset == 144
     assert C.sizeof(_abi.PtgTables) == 17 * 8 * 2 + 6 * 8
     assert C.sizeof(_abi.PtgIO) == 8 * 8
     assert C.sizeof(_abi.PtgObsKey) == 40
     assert C.sizeof(_abi.PtgEpisodeStats) == 64
-    assert C.sizeof(_abi.PtgStateSoA) == 16 * 8
+    assert C.sizeof(_abi.PtgStateSoA) == 18 * 8
 
 
 def test_stats_combine_host():

@@ -433,3 +433,116 @@ def test_single_env_gymnasium_interface_matches_reference_golden():
     obs, _ = env.reset()
     assert obs["METH_STATUS"] == 1
     env.close()
+
+
+def test_single_env_gymnasium_interface_on_the_training_split():
+    """gym_env.PTGEnv through three terminated -> reset() cycles on the TRAINING split against ONE unmodified
+    reference env (tests/golden/single_env_train_resets.npz): the constructor consumes eps_ind[0], every reset() the
+    next entry -- never two per episode (the VecEnv's auto-reset is off behind this interface)."""
+    from helpers import real_kwargs
+    from rl_ptg_b200.gym_env import PTGEnv
+    from test_oracle_golden import load_single_env_golden
+    g = load_single_env_golden()
+    m = g["meta"]
+    kw = real_kwargs(m["overrides"], m["split"], m["action_type"], m["seed_train"])
+    env = PTGEnv(kw, "train")
+    assert (env.act_ep_h, env.act_ep_d) == tuple(g["offsets"][0])
+    from rl_ptg_b200 import _abi
+    obs_keys = [k for k, _, _ in _abi.obs_keys("mod", int(kw["price_ahead"]))]
+    flat = lambda o: np.concatenate([np.atleast_1d(np.asarray(o[k], dtype=np.float64)).ravel() for k in obs_keys])   # noqa: E731
+    keep = {int(t): q for q, t in enumerate(g["obs_steps"])}
+    t = 0
+    for ep in range(m["episodes"]):
+        obs, info = env.reset(seed=m["seed"]) if ep == 0 else env.reset()
+        assert (env.act_ep_h, env.act_ep_d) == tuple(g["offsets"][ep + 1]), f"episode {ep}: wrong eps_ind entry"
+        assert_close_fp32(flat(obs), g["reset_obs"][ep], f"reset obs {ep}")
+        assert len(info) == 24 and info["step"] == 0
+        for q in range(m["ep_len"]):
+            obs, rew, terminated, truncated, info = env.step(int(g["actions"][t]))
+            assert info == {} and truncated is False
+            assert terminated == bool(g["ints"][t, 4]), f"terminated at step {t}"
+            assert_close_fp32(np.float64(rew), g["rewards"][t], f"reward step {t}")
+            if t in keep:
+                assert_close_fp32(flat(obs), g["obs"][keep[t]], f"obs step {t}")
+                got = (env.Meth_State, env.i, env.j, env.hot_cold, env.k)
+                assert got == tuple(int(v) for v in g["ints"][t][[0, 1, 2, 3, 5]]), f"plant state at step {t}"
+            t += 1
+        assert terminated
+        assert_close_fp32(flat(obs), g["term_obs"][ep], f"terminal obs {ep}")
+    env.close()
+
+
+def test_restored_env_continues_bit_identically_under_device_noise():
+    """get_state -> set_state into a FRESH env (different seeds, different history) under the default on-device numpy
+    noise and a state-change penalty: the restored env and the original then produce identical trajectories, noise
+    stream and eval-mode cum_reward included (the snapshot carries the PCG64 words and the state-change counter)."""
+    kw = synthetic_kwargs(dict(scenario=1, operation="OP2", state_change_penalty=0.3))
+    n = 777
+    env = make_env(kw, n, seed=11, train_or_eval="eval")
+    env.reset()
+    rng = np.random.default_rng(2)
+    for t in range(60):
+        env.step(rng.integers(0, 5, size=n))
+    snap = env.get_state()
+    assert snap["rng"].shape == (n, 4) and snap["state_changes"].max() > 0 and snap["draws"].max() > 0
+    other = make_env(kw, n, seed=999, train_or_eval="eval")
+    other.reset()
+    for t in range(7):
+        other.step(rng.integers(0, 5, size=n))
+    other.set_state(snap)
+    back = other.get_state()
+    for f in snap:
+        assert np.array_equal(snap[f], back[f]), f
+    for t in range(80):
+        a = rng.integers(0, 5, size=n)
+        o1, r1, d1, i1 = env.step(a)
+        o2, r2, d2, i2 = other.step(a)
+        assert np.array_equal(r1, r2) and np.array_equal(d1, d2), f"step {t}"
+        for k in o1:
+            assert np.array_equal(o1[k], o2[k]), f"{k} step {t}"
+        assert i1[5]["cum_reward"] == i2[5]["cum_reward"] and i1[n - 1]["reward [ct]"] == i2[n - 1]["reward [ct]"]
+    s1, s2 = env.get_state(), other.get_state()
+    for f in INT_FIELDS + ("rng", "state_changes", "cum_reward"):
+        assert np.array_equal(s1[f], s2[f]), f
+    env.close(); other.close()
+
+
+def test_graph_replay_invalidates_the_host_window_mirror():
+    """numpy step -> graph.replay() (crosses hours) -> numpy step that does not cross an hour itself: the window
+    blocks handed out must be the current ones (the replay bypasses step_wait)."""
+    import torch
+    kw = synthetic_kwargs(dict(scenario=2, operation="OP2"))
+    n = 512
+    env, ref = make_env(kw, n, seed=3), make_env(kw, n, seed=3)
+    env.reset(); ref.reset()
+    rng = np.random.default_rng(9)
+    acts = [rng.integers(0, 5, size=n) for _ in range(9)]
+    env.step(acts[0]); ref.step(acts[0])
+    bufs = [torch.as_tensor(a, device=env.device) for a in acts[1:8]]          # 7 steps: crosses an hour (6 steps)
+    graph = env.capture_steps(bufs)       # (the capture's warm-up step runs acts[1] once outside the graph)
+    ref.step(acts[1])
+    graph.replay()
+    for a in acts[1:8]:
+        ref.step(a)
+    o1, r1, _, _ = env.step(acts[8])
+    o2, r2, _, _ = ref.step(acts[8])
+    assert np.array_equal(r1, r2)
+    for k in o1:
+        assert np.array_equal(o1[k], o2[k]), k
+    env.close(); ref.close()
+
+
+def test_step_on_a_foreign_current_device_is_refused():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from rl_ptg_b200._lib import PtgError
+    env = make_env(synthetic_kwargs(), 64, seed=1)
+    env.reset()
+    a = torch.zeros(64, dtype=torch.int64, device=env.device)
+    with torch.cuda.device(1):
+        with pytest.raises(PtgError) as ei:
+            env.step_tensor(a)
+    assert ei.value.code == -1 and "current CUDA device" in str(ei.value)
+    env.step_tensor(a)
+    env.close()

@@ -3,6 +3,8 @@ and against the CPU oracle on identical actions / seeds.
 
 Bar (BASELINE.json north_star): bit-exact plant state, indices, episode offsets and termination flags;
 observations and rewards within 1e-5 relative in fp32 (tolerance written below); exact zeros stay exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -209,3 +211,74 @@ def test_invalid_action_and_closed_env_fail_loudly():
     env.close()
     with pytest.raises(RuntimeError):
         env.step(np.zeros(64, dtype=np.int64))
+
+
+def _oracle_features(obs: np.ndarray, pa: int) -> np.ndarray:
+    """Oracle observation rows (reference key order) -> SB3 CombinedExtractor feature rows (sorted keys, one-hot
+    METH_STATUS), the layout obs_layout="flat" writes."""
+    n = obs.shape[0]
+    f = np.zeros((n, 14 + 2 * pa))
+    o_st = 2 * pa
+    o_T, o_h2, o_ch4, o_h2res, o_h2o, o_heat, o_sin, o_cos = (2 * pa + 1 + q for q in range(8))
+    f[:, 0], f[:, 1], f[:, 2], f[:, 3], f[:, 4] = obs[:, o_ch4], obs[:, o_heat], obs[:, o_h2o], obs[:, o_h2], obs[:, o_h2res]
+    f[np.arange(n), 5 + obs[:, o_st].astype(np.int64)] = 1.0
+    f[:, 11:11 + pa], f[:, 11 + pa:11 + 2 * pa] = obs[:, pa:2 * pa], obs[:, :pa]
+    f[:, 11 + 2 * pa], f[:, 12 + 2 * pa], f[:, 13 + 2 * pa] = obs[:, o_T], obs[:, o_cos], obs[:, o_sin]
+    return f
+
+
+@pytest.mark.parametrize("layout", ["dict", "flat"])
+def test_benchmarked_workload_matches_oracle(layout):
+    """The workload bench.py times -- synthetic BS2/OP2 `mod`, uniform random discrete actions, seeds 3654 + i, numpy
+    noise on the device -- at 65 536 envs against the CPU oracle: every step's rewards, dones and FULL observations
+    across eight hour crossings, one episode end (eps_sim_steps shortened to 46), terminal observations and the
+    auto-reset rows.  `flat`: the same against the oracle rows re-ordered to the feature layout (not against the
+    dict layout)."""
+    import torch
+    from oracle.ptg_oracle import OracleVecEnv, draw_noise_tape
+    kw = dict(synthetic_kwargs(dict(scenario=2, operation="OP2")))
+    kw["eps_sim_steps"] = 46                      # episodes of 41 steps
+    n, steps, pa = 65536, 50, int(kw["price_ahead"])
+    seeds = 3654 + np.arange(n)
+    ora = OracleVecEnv(kw, n, noise_tape=draw_noise_tape(seeds, kw["noise"], steps), threads=len(os.sched_getaffinity(0)))
+    env = make_env(kw, n, seed=3654, obs_layout=layout)
+    o_obs = ora.reset().copy()
+    rng = np.random.default_rng(0)
+    if layout == "dict":
+        obs = env.reset()
+        keys = list(obs.keys())
+        assert_close_fp32(flat_obs(obs, keys), o_obs, "reset obs")
+    else:
+        env.reset_tensor()
+        assert_close_fp32(env.features_view().cpu().numpy(), _oracle_features(o_obs, pa), "reset rows")
+    n_done = 0
+    for t in range(steps):
+        a = rng.integers(0, 5, size=n)
+        o_obs, o_rew, o_done = ora.step(a)
+        if layout == "dict":
+            obs, rew, done, infos = env.step(a)
+            got = flat_obs(obs, keys)
+            want = o_obs
+        else:
+            _, rew_t, done_t = env.step_tensor(torch.as_tensor(a, device=env.device))
+            rew, done = rew_t.cpu().numpy(), done_t.cpu().numpy().astype(bool)
+            got, want = env.features_view().cpu().numpy(), _oracle_features(o_obs, pa)
+        assert np.array_equal(done, o_done.astype(bool)), f"done step {t}"
+        assert_close_fp32(rew, o_rew, f"reward step {t}")
+        assert_close_fp32(got, want, f"obs step {t}")
+        if o_done.any():
+            n_done += int(o_done.sum())
+            idx = np.nonzero(o_done)[0]
+            if layout == "dict":
+                term = np.stack([np.concatenate([np.atleast_1d(np.asarray(infos[e]["terminal_observation"][k], np.float64)).ravel()
+                                                 for k in keys]) for e in idx[:64]])
+                assert_close_fp32(term, ora.terminal_obs[idx[:64]], "terminal obs")
+                assert infos[int(idx[0])]["episode"]["r"] == pytest.approx(ora.episode_return[idx[0]], abs=1e-6)
+            else:
+                term = env._term_obs[:n * env.feature_dim].view(n, env.feature_dim).cpu().numpy()
+                assert_close_fp32(term[idx], _oracle_features(ora.terminal_obs[idx], pa), "terminal rows")
+    assert n_done == n                            # every env ended exactly one episode
+    so, sg = ora.get_state(), env.get_state()
+    for f in ("meth_state", "i", "j", "k", "hot_cold", "partial_ds", "full_ds", "act_ep_h", "act_ep_d", "episode_count", "draws"):
+        assert np.array_equal(so[f], sg[f]), f
+    env.close(); ora.close()

@@ -48,3 +48,45 @@ def test_oracle_matches_reference(case):
 def test_zero_reward_in_cold_cooldown_is_exact():
     g = load_golden("bs2_op2_mod")
     assert g["rewards"][0, 0] == 0.0 and g["rewards"][1, 0] == 0.0
+
+
+def load_single_env_golden():
+    import json
+    import os
+    from helpers import GOLDEN_DIR
+    with np.load(os.path.join(GOLDEN_DIR, "single_env_train_resets.npz"), allow_pickle=False) as z:
+        g = {k: z[k] for k in z.files}
+    g["meta"] = json.loads(str(g["meta"]))
+    return g
+
+
+def test_oracle_single_env_gymnasium_semantics_on_the_training_split():
+    """ONE env, no auto-reset, three terminated -> reset() cycles on the training split: the constructor uses
+    eps_ind[0], the resets [1], [2], [3] (env/ptg_gym_env.py:59-62, 490-493; golden from the unmodified reference)."""
+    from helpers import real_kwargs
+    g = load_single_env_golden()
+    m = g["meta"]
+    kw = real_kwargs(m["overrides"], m["split"], m["action_type"], m["seed_train"])
+    assert np.array_equal(kw["eps_ind"][:8], g["eps_ind_head"])
+    tape = draw_noise_tape([m["seed"]], kw["noise"], len(g["actions"]))
+    env = OracleVecEnv(kw, 1, noise_tape=tape)
+    st = env.get_state()
+    assert (st["act_ep_h"][0], st["act_ep_d"][0]) == tuple(g["offsets"][0])
+    keep = {int(t): q for q, t in enumerate(g["obs_steps"])}
+    t = 0
+    for ep in range(m["episodes"]):
+        obs = env.reset()
+        st = env.get_state()
+        assert (st["act_ep_h"][0], st["act_ep_d"][0]) == tuple(g["offsets"][ep + 1]), f"episode {ep} schedule"
+        assert np.array_equal(obs[0], g["reset_obs"][ep])
+        assert np.allclose(env.info[0], g["reset_info"][ep], rtol=FP64_TOL, atol=0)
+        for _ in range(m["ep_len"]):
+            obs, rew, done = env.step(g["actions"][t:t + 1].astype(np.int64), auto_reset=False)
+            st = env.get_state()
+            got = (st["meth_state"][0], st["i"][0], st["j"][0], st["hot_cold"][0], int(done[0]), st["k"][0])
+            assert got == tuple(g["ints"][t]), f"integer state diverged at step {t}"
+            assert rew[0] == pytest.approx(g["rewards"][t], rel=FP64_TOL, abs=0)
+            if t in keep:
+                assert np.allclose(obs[0], g["obs"][keep[t]], rtol=FP64_TOL, atol=1e-15)
+            t += 1
+        assert done[0] == 1 and np.allclose(obs[0], g["term_obs"][ep], rtol=FP64_TOL, atol=1e-15)
