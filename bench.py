@@ -13,10 +13,17 @@ One "step" = one VecEnv step over every env (one k_step launch per rank).
             observations, rewards and dones inside the timed region
   roofline  algorithmic HBM bytes per env-step (ptg_bytes_per_env_step) x envs / kernel time (CUDA
             events around the timed region on the launching stream) vs the measured copy peak
-  cpu_baseline  the CPU oracle (a literal C restatement of the reference PTGEnv) on all host cores, bounded sample
+  cpu_baseline  the UNMODIFIED Python reference PTGEnv (baseline/_ref, staged by tools/stage_reference.sh) on this
+            box's host cores: SubprocVecEnv-style lock-step over all cores + one env / one episode in-process, with
+            the SHA-256 of its (Meth_State, i, j, hot_cold, terminated) trajectory compared with the CUDA path's;
+            the compiled C oracle port is reported beside it as cpu_baseline_port
+  config.strong_scaling  BASELINE config 4 as written: 1,048,576 envs IN TOTAL over the ranks, the episode-statistics
+            all-gather (ptg_allreduce_stats, NCCL) once per 32-step roll-out inside the timed loop
 
-`--impl reference` times that CPU oracle as the reference arm (the reference itself is Python and cannot travel
-to the GPU box; tests/ pin the oracle bit-exactly to it).
+The timed region follows an untimed pre-roll (600 steps, stationary plant-state mix) and >= 10 ms of untimed single
+steps, so a 20-step run measures the same steady state as a 4000-step run.
+
+`--impl reference` times the unmodified Python reference under the SubprocVecEnv-style harness as the reference arm.
 """
 from __future__ import annotations
 
@@ -41,6 +48,7 @@ ENVS_PER_GPU = 1 << 20
 RNG_BYTES_PER_DRAW = 48
 WORKLOAD = "BS2/OP2 mod, discrete int64 actions, train episodes, synthetic data of repo shapes"
 METRIC, UNIT = "env-steps/sec", "env-steps/s"
+REF_LOCK_STEPS_PER_STEP = 100     # reference arm: one bench "step" = this many lock-steps of the Python reference
 
 
 def make_kwargs(scenario=2, operation="OP2"):
@@ -111,28 +119,167 @@ def cpu_oracle_rate(kw, n_envs: int, lock_steps: int, threads: int, warm: int = 
     return n_envs * lock_steps / dt, dt
 
 
+def episode_action_tape(kw) -> np.ndarray:
+    """the fixed action tape of config 1 -- default_rng(0).integers(0, 5, eps_sim_steps), of which
+    one training episode (eps_sim_steps - 5 steps) is used."""
+    return np.random.default_rng(0).integers(0, 5, size=int(kw["eps_sim_steps"]))[:int(kw["eps_sim_steps"]) - 5]
+
+
+def reference_python_baseline(kw, cores: int, lock_steps: int, repeats: int = 3, record: bool = True) -> dict:
+    """The UNMODIFIED reference `PTGEnv` (env/ptg_gym_env.py, imported from baseline/_ref through the gymnasium stub)
+    timed on this box's host cores in the two arrangements of SURVEY.md 8(d) / BASELINE.md section 3:
+      (i)  config 1: ONE env, one training episode, fixed action tape, in-process, best of `repeats`
+      (ii) SubprocVecEnv-style lock-step: `cores` forked workers over pipes, in-worker auto-reset, `lock_steps` steps
+    plus the reference's default arrangement (DummyVecEnv, 6 envs in one process)."""
+    from oracle import ref_bench
+    acts = episode_action_tape(kw)
+    best, n_steps, sha, ends = ref_bench.single_env_episode(kw, acts, 3654, record=record, repeats=repeats)
+    sub_rate, sub_dt = ref_bench.subproc_rate(kw, cores, lock_steps)
+    dummy_rate, _ = ref_bench.dummy_rate(kw, 6, max(50, lock_steps // 8))
+    return {"single_env_steps_per_s": n_steps / best, "single_env_episode_s": best, "single_env_steps": n_steps,
+            "single_env_episode_ends": ends, "trajectory_sha256": sha,
+            "subproc_steps_per_s": sub_rate, "subproc_workers": cores, "subproc_lock_steps": lock_steps,
+            "subproc_seconds": sub_dt, "dummy6_steps_per_s": dummy_rate, "root": ref_bench.reference_root()}
+
+
+def reference_headline(ref: dict):
+    """The reference figure the GPU path is compared with: the FASTEST of the reference's own arrangements on this box
+    (SubprocVecEnv over all cores as the north star names it; DummyVecEnv with 6 envs, the reference's default; one env
+    in-process) -- pipes and pickling make Subproc the slowest of the three on some hosts."""
+    cands = {"SubprocVecEnv-style, one env per core": ref["subproc_steps_per_s"],
+             "DummyVecEnv, 6 envs in one process": ref["dummy6_steps_per_s"],
+             "one env in-process": ref["single_env_steps_per_s"]}
+    which = max(cands, key=cands.get)
+    return cands[which], which
+
+
 def run_reference(args):
-    """Reference arm: the CPU implementation of the path on the host cores (oracle port; see module docstring)."""
+    """Reference arm: the reference's own CPU implementation of the path -- the unmodified Python `PTGEnv` under a
+    SubprocVecEnv-style harness on all host cores (`parallel: Multiprocessing`, src/rl_utils.py:484-486).  One "step"
+    of this arm is a bounded sample of REF_LOCK_STEPS_PER_STEP lock-steps over `cores` envs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
     kw = make_kwargs()
-    n_envs = 4096 * max(1, cores // 4)
-    # each "step" = one lock-step of the bounded sample; keep the whole run within a few minutes
-    args.steps = min(args.steps, 300)       # one lock-step of the sample takes ~15 ms; keep the arm within minutes
-    rate, dt = cpu_oracle_rate(kw, n_envs, max(1, args.steps), cores, warm=max(1, min(args.warmup, 5)))
+    from oracle import ref_bench
+    if ref_bench.reference_root() is None:          # (never on a box that received baseline/_ref; kept loud, not silent)
+        rate, dt = cpu_oracle_rate(kw, 4096 * max(1, cores // 4), 100, cores)
+        _emit({"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": WORKLOAD, "note": "baseline/_ref missing (run tools/stage_reference.sh): CPU oracle port timed instead"},
+               "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": "oracle port"},
+               "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+        return
+    K = max(1, min(args.steps, 60))
+    W = max(1, min(args.warmup, 10))
+    lock_steps = K * REF_LOCK_STEPS_PER_STEP
+    ref = reference_python_baseline(kw, cores, lock_steps, repeats=3, record=True)
+    port_rate, _ = cpu_oracle_rate(kw, 4096 * max(1, cores // 4), 60, cores)
+    rate, which = reference_headline(ref)
+    sample = (f"unmodified reference PTGEnv, {cores} forked workers (SubprocVecEnv protocol over pipes, in-worker "
+              f"auto-reset), {lock_steps} lock-steps = {ref['subproc_seconds']:.1f} s, uniform random actions; value = "
+              f"the fastest of the reference's arrangements on this box ({which})")
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * ref["subproc_seconds"] / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs": n_envs, "sample": f"{n_envs} envs x {args.steps} lock-steps"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_envs} envs x {args.steps} lock-steps, uniform random actions, tape noise"},
+        "config": {"workload": WORKLOAD, "envs": cores, "lock_steps_per_step": REF_LOCK_STEPS_PER_STEP,
+                   "arrangement": "SubprocVecEnv-style (parallel: Multiprocessing), one reference env per host core; also "
+                                  "DummyVecEnv with 6 envs (the reference's default) and one env in-process",
+                   "arrangement_reported": which,
+                   "reference": ref,
+                   "cpu_oracle_port_steps_per_s": port_rate},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(line)
+
+
+def cuda_trajectory_sha(kw, dev) -> str:
+    """SHA-256 of the per-step (Meth_State, i, j, hot_cold, terminated) record of ONE env on the CUDA path for the
+    config-1 episode (seed 3654, the fixed action tape, numpy-exact noise on the device) -- compared with the same
+    record of the unmodified reference env (reference_python_baseline)."""
+    import hashlib
+    from rl_ptg_b200.vec_env import PtGVecEnv
+    acts = episode_action_tape(kw)
+    env = PtGVecEnv(kw, 1, seed=3654, device=dev, auto_reset=False)
+    env.reset()
+    rec = np.zeros((len(acts), 5), dtype=np.int64)
+    for t, a in enumerate(acts):
+        _, _, done, _ = env.step(np.array([a]))
+        st = env.get_state()
+        rec[t] = (st["meth_state"][0], st["i"][0], st["j"][0], st["hot_cold"][0], int(done[0]))
+    env.close()
+    return hashlib.sha256(rec.tobytes()).hexdigest()
+
+
+def strong_scaling_leg(kw, dev, world, rank, peak, draws_per_step, n_total=1 << 20, T=32, rollouts=8):
+    """BASELINE config 4 as written: 1 048 576 envs IN TOTAL, sharded over the ranks, with the episode-statistics
+    reduction (ptg_episode_stats + ptg_allreduce_stats: one NCCL all-gather of the 64-byte record + combine, inside
+    the library) issued once per T-step roll-out INSIDE the timed loop.  Episodes are shortened (257 steps) in this
+    leg so that the gathered record is non-zero.  Three ways to issue the T steps of a roll-out."""
+    import torch
+    import torch.distributed as dist
+    from rl_ptg_b200.vec_env import PtGVecEnv, shard_range, stats_dict
+    lo, hi = shard_range(n_total, rank, world)
+    n = hi - lo
+    kws = dict(kw)
+    kws["eps_sim_steps"] = 262
+    env = PtGVecEnv(kws, n, seed=3654, device=dev, env_id_offset=lo, n_envs_global=n_total)
+    env.reset_tensor()
+    g = torch.Generator(device=dev)
+    g.manual_seed(99 + rank)
+    acts = torch.randint(0, 5, (T, n), generator=g, device=dev, dtype=torch.int64)
+    out = env.rollout_tensor(acts)                      # also the pre-roll: 2 x T steps
+    env.rollout_tensor(acts, out=out)
+    graph = env.capture_steps([acts[t] for t in range(T)])
+    stats_h = torch.zeros((rollouts, 8), dtype=torch.float64).pin_memory()
+    bpe0 = env.bytes_per_env_step
+    bpe_single = bpe0 + RNG_BYTES_PER_DRAW * draws_per_step
+    bpe_many = bpe_single - 64 + 64 / T
+    res = {}
+
+    def eager():
+        for t in range(T):
+            env.step_tensor(acts[t])
+
+    modes = (("eager_ptg_step", eager, bpe_single), ("cuda_graph_of_ptg_step", graph.replay, bpe_single),
+             ("ptg_step_many", lambda: env.rollout_tensor(acts, out=out), bpe_many))
+    for name, issue, bpe in modes:
+        for _ in range(2):                              # warm-up roll-outs (and a first use of the communicator)
+            issue()
+            env.episode_stats_async(clear=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(rollouts):
+            issue()
+            rec = env.episode_stats_async(clear=True)   # device reduction + NCCL all-gather + combine, in stream
+            stats_h[r].copy_(rec, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_step = float(ms.item()) / (rollouts * T)
+        tot = stats_h.numpy()
+        res[name] = {"ms_per_step": ms_step, "env_steps_per_s_total": n_total / (ms_step * 1e-3),
+                     "bytes_per_env_step": round(bpe, 2),
+                     "roofline_frac": bpe * n / (ms_step * 1e-3) / 1e9 / peak,
+                     "episodes_in_gathered_records": int(tot[:, 0].sum()),
+                     "env_steps_in_gathered_records": int(tot[:, 6].sum())}
+    last = stats_dict(stats_h[-1].numpy(), world)
+    env.close()
+    return {"envs_total": n_total, "envs_per_gpu": n, "T": T, "rollouts_timed": rollouts,
+            "collective": "ptg_episode_stats + ptg_allreduce_stats (ncclAllGather of 64 B + combine kernel) once per "
+                          "roll-out inside the timed loop" if world > 1 else
+                          "ptg_episode_stats once per roll-out inside the timed loop (one rank: nothing to gather)",
+            "episode_length_in_this_leg": 257, "modes": res, "last_record": last}
 
 
 def run_gpu(args):
@@ -145,6 +292,10 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cores = len(os.sched_getaffinity(0))
+    # torchrun exports OMP_NUM_THREADS=1: give every rank its share of the host cores for the converting copies
+    host_threads = max(1, cores // world)
+    torch.set_num_threads(host_threads)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -166,53 +317,67 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing (value, roofline) ----------------
     def total_draws():
         return int(env.get_state()["draws"].sum())
 
-    def timed(pool_, n_steps):
-        for t in range(W):
-            env.step_tensor(pool_[t % n_pool])
-        torch.cuda.synchronize()
+    # ---------------- untimed pre-roll to a stationary plant-state mix ----------------
+    # A fresh batch has every env in cooldown at the same table row; the mix of plant states (and with it the gather
+    # pattern and the draw rate) only becomes stationary after a few hundred random steps.  ptg_step_many, T = 8.
+    T_pre = 8
+    acts_pre = pool[:T_pre].contiguous()
+    out_pre = env.rollout_tensor(acts_pre)
+    for _ in range(max(0, args.preroll_steps // T_pre - 1)):
+        env.rollout_tensor(acts_pre, out=out_pre)
+    del out_pre
+    preroll_done = max(1, args.preroll_steps // T_pre) * T_pre
+    torch.cuda.synchronize()
+
+    def timed(pool_, n_steps, pre):
+        """`pre` untimed single steps (>= 10 ms: clocks and caches in their steady state), then n_steps timed ones."""
         d0 = total_draws()
+        for t in range(pre):
+            env.step_tensor(pool_[t % n_pool])
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         for t in range(n_steps):
-            env.step_tensor(pool_[t % n_pool])
+            env.step_tensor(pool_[(pre + t) % n_pool])
         a1.record()
         torch.cuda.synchronize()
-        return a0.elapsed_time(a1) / n_steps, (total_draws() - d0) / (n_steps * n_local)
+        return a0.elapsed_time(a1) / n_steps, (total_draws() - d0) / ((pre + n_steps) * n_local)
 
-    for t in range(W):
-        env.step_tensor(pool[t % n_pool])
-    draws0 = total_draws()
-    barrier()
+    # ---------------- headline: K single steps, device-resident inputs ----------------
+    P = max(W, args.presteps)                            # untimed single steps right in front of the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    draws0 = total_draws()
+    for t in range(P):
+        env.step_tensor(pool[t % n_pool])
+    barrier()
     l0 = env.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for t in range(K):
-        env.step_tensor(pool[t % n_pool])
+        env.step_tensor(pool[(P + t) % n_pool])
     ev1.record()
     barrier()
     launches = env.kernel_launches() - l0
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    draws_per_step = (total_draws() - draws0) / (K * n_local)
+    draws_per_step = (total_draws() - draws0) / ((P + K) * n_local)
     # secondary action distributions (SURVEY.md 8(d)): the load-biased mix, and an agent-like "sticky" policy (each
     # env repeats one action, so almost no transition noise is drawn after warm-up)
-    Ks = max(50, K // 4)
+    Ks = max(200, K)
     probs = torch.tensor([.05, .05, .3, .3, .3], device=dev)
     biased = torch.multinomial(probs, n_pool * n_local, replacement=True, generator=g).view(n_pool, n_local)
-    biased_ms, biased_draws = timed(biased, Ks)
+    biased_ms, biased_draws = timed(biased, Ks, 400)
     del biased
     sticky = pool[:1].repeat(n_pool, 1).contiguous()
-    sticky_ms, sticky_draws = timed(sticky, Ks)
+    sticky_ms, sticky_draws = timed(sticky, Ks, 400)
     del sticky
+    long_ms, _ = timed(pool, max(1000, K), 200)          # the same uniform workload over a long timed region
+    clocks = sampler.stop() if rank == 0 else None
     env.poll_error()
-    stats = env.episode_stats(clear=True)       # the path's only collective: one 64-byte all-gather per roll-out
+    stats = env.episode_stats(clear=True)
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -221,14 +386,15 @@ def run_gpu(args):
     # ---------------- rollout kernel (T steps per launch), reported in config ----------------
     T = 16
     acts_T = pool[:min(T, n_pool)].repeat((T + n_pool - 1) // n_pool, 1)[:T].contiguous()
-    out = None
     roll_ms = None
     if args.rollout:
         out = env.rollout_tensor(acts_T)
+        for _ in range(8):
+            env.rollout_tensor(acts_T, out=out)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        reps = max(1, K // T)
+        reps = max(8, K // T)
         for _ in range(reps):
             env.rollout_tensor(acts_T, out=out)
         e1.record()
@@ -239,7 +405,7 @@ def run_gpu(args):
     # ---------------- end to end through the numpy API ----------------
     acts_h = [pool[q].cpu().numpy() for q in range(n_pool)]
     Ke = max(3, min(K, args.e2e_steps))
-    for t in range(3):
+    for t in range(6):
         env.step(acts_h[t % n_pool])
     barrier()
     d2h0 = env.d2h_bytes
@@ -253,13 +419,21 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e.item())
-    h2d = n_local * 8
+    h2d = env.h2d_bytes_per_step
     d2h = d2h_measured          # counted from the tensors copied: the window blocks travel only when they changed
     d2h_full = env.obs_elems * 4 + n_local * 4 + n_local
+    bpe0 = env.bytes_per_env_step
+    obs_dim = env.obs_dim
+    env.close()
+    del pool
+
+    # ---------------- BASELINE config 4 as written: 1M envs in total over the ranks, collective in the timed loop
+    peak, peak_src = measured_peak_gbs()
+    strong = None
+    if args.strong:
+        strong = strong_scaling_leg(kw, dev, world, rank, peak, draws_per_step)
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        bpe0 = env.bytes_per_env_step                        # state + action + observation + reward/done
         bpe = bpe0 + RNG_BYTES_PER_DRAW * draws_per_step     # + the RNG state of the env-steps that draw noise
         kernel_ms = ms / K                                   # rank 0's own kernel time (CUDA events, same stream)
         achieved = bpe * n_local / (kernel_ms * 1e-3) / 1e9
@@ -273,31 +447,47 @@ def run_gpu(args):
         if tps:
             with open(os.path.join(ROOT, "profiles", tps[-1])) as fh:
                 traffic = json.load(fh).get("dram_bytes_per_launch")
-        cores = len(os.sched_getaffinity(0))
-        cpu = None
+        cpu = cpu_port = None
         if world == 1 and not args.no_cpu_baseline:
+            from oracle import ref_bench
             n_cpu = 4096 * max(1, cores // 4)
-            probe, _ = cpu_oracle_rate(kw, n_cpu, 10, cores, warm=2)                  # size the sample to ~15 s
-            args.cpu_lock_steps = int(min(2000, max(20, args.cpu_seconds * probe / n_cpu)))
-            rate, dt = cpu_oracle_rate(kw, n_cpu, args.cpu_lock_steps, cores)
-            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"CPU oracle (C restatement of PTGEnv, pthreads), {n_cpu} envs x {args.cpu_lock_steps} "
-                             f"lock-steps = {dt:.1f} s",
-                   "note": "a compiled port: the Python reference itself steps ~1.0e4 env-steps/s per core and "
-                           "~9.6e3 in total under an 8-process SubprocVecEnv-style harness (BASELINE.md section 2)"}
+            port_rate, port_dt = cpu_oracle_rate(kw, n_cpu, 60, cores, warm=2)
+            cpu_port = {"value": port_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"CPU oracle (C restatement of PTGEnv, pthreads), {n_cpu} envs x 60 lock-steps = {port_dt:.1f} s"}
+            if ref_bench.reference_root() is not None:
+                ref = reference_python_baseline(kw, cores, args.cpu_lock_steps, repeats=3, record=True)
+                sha_cuda = cuda_trajectory_sha(kw, dev)
+                ref_value, ref_which = reference_headline(ref)
+                cpu = {"value": ref_value, "unit": UNIT, "cores": cores, "kind": "reference",
+                       "arrangement_reported": ref_which, "subproc_steps_per_s": ref["subproc_steps_per_s"],
+                       "sample": f"unmodified reference PTGEnv (baseline/_ref): {cores} forked workers, SubprocVecEnv "
+                                 f"protocol over pipes, {args.cpu_lock_steps} lock-steps = {ref['subproc_seconds']:.1f} s; "
+                                 f"+ one env, one {ref['single_env_steps']}-step training episode, best of 3 = "
+                                 f"{ref['single_env_episode_s']:.2f} s",
+                       "single_env_steps_per_s": ref["single_env_steps_per_s"],
+                       "dummy_vec_env_6_steps_per_s": ref["dummy6_steps_per_s"],
+                       "trajectory_sha256_reference": ref["trajectory_sha256"], "trajectory_sha256_cuda": sha_cuda,
+                       "trajectory_match": ref["trajectory_sha256"] == sha_cuda}
+            else:
+                cpu = dict(cpu_port, note="baseline/_ref missing on this box (tools/stage_reference.sh): port timed instead")
         line = {
             "metric": METRIC, "value": n_global * K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": n_local, "envs_total": n_global,
-                       "obs_dim": env.obs_dim, "noise": "on-device PCG64+ziggurat (numpy-exact)",
+                       "obs_dim": obs_dim, "noise": "on-device PCG64+ziggurat (numpy-exact)",
+                       "preroll_steps": preroll_done, "untimed_single_steps_before_timed_region": P,
                        "bytes_per_env_step": round(bpe, 2),
                        "bytes_per_env_step_breakdown": {"state_action_obs_reward_done": bpe0,
                                                         "rng_state_per_draw": RNG_BYTES_PER_DRAW,
                                                         "draws_per_env_step": round(draws_per_step, 4)},
-                       "l2": f"per-step traffic {bpe * n_local / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
-                       "actions": "uniform random over the 5 actions (worst case: ~38% of env-steps redraw noise)",
+                       "l2": f"per-step traffic {bpe * n_local / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2); plant "
+                             "state, RNG records and tables are kept L2-resident on purpose (evict_last), observations "
+                             "/ rewards / actions stream (evict_first)",
+                       "actions": "uniform random over the 5 actions (worst case: ~40% of env-steps redraw noise)",
                        "roofline_frac_excluding_rng_bytes": bpe0 * n_local / (kernel_ms * 1e-3) / 1e9 / peak,
+                       "uniform_long_run": {"steps": max(1000, K), "ms_per_step": long_ms,
+                                            "roofline_frac": frac_of(long_ms, draws_per_step)},
                        "load_biased_mix": {"p": [.05, .05, .3, .3, .3], "ms_per_step": biased_ms,
                                            "draws_per_env_step": round(biased_draws, 4),
                                            "roofline_frac": frac_of(biased_ms, biased_draws)},
@@ -307,20 +497,23 @@ def run_gpu(args):
                            "T": T, "ms_per_step": roll_ms,
                            "bytes_per_env_step": round(bpe - 64 + 64 / T, 2),     # state stays in registers between steps
                            "roofline_frac": (bpe - 64 + 64 / T) * n_local / (roll_ms * 1e-3) / 1e9 / peak},
+                       "strong_scaling": strong,
+                       "host_threads_per_rank": host_threads,
                        "episodes_finished": stats["episodes"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_step<4,true,false,false,13>",
                          "kernel_ms": kernel_ms},
             "cpu_baseline": cpu,
+            "cpu_baseline_port": cpu_port,
             "e2e": {"value": n_global * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "d2h_bytes_per_step_if_every_block_travelled": d2h_full,
-                    "steps": Ke, "note": "numpy VecEnv.step(); the market-window blocks (109 of 147 MB) are re-read "
-                                         "only on steps that move them (clock crosses an hour / episode end)"},
+                    "steps": Ke, "note": "numpy VecEnv.step(): int64 action array in, converted to uint8 on the wire; "
+                                         "the market-window blocks (109 of 147 MB) are re-read only on steps that "
+                                         "move them (clock crosses an hour / episode end)"},
             "gpu_launches": launches,
             "clocks": clocks,
         }
         _emit(line)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -496,13 +689,16 @@ def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--preroll-steps", type=int, default=600, help="untimed ptg_step_many steps to a stationary state mix")
+    ap.add_argument("--presteps", type=int, default=1024, help="untimed single steps right before the timed region (>= 10 ms)")
+    ap.add_argument("--strong", action="store_true", default=True, help="BASELINE config 4 leg: 1M envs in total")
+    ap.add_argument("--no-strong", dest="strong", action="store_false")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=60)
-    ap.add_argument("--cpu-lock-steps", type=int, default=150)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-lock-steps", type=int, default=2000, help="lock-steps of the Python reference under the Subproc harness")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rollout", action="store_true", default=True)
     ap.add_argument("--no-rollout", dest="rollout", action="store_false")

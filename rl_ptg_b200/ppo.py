@@ -121,6 +121,14 @@ class PPOCore:
         import torch.distributed as dist
         self._world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         if self._world > 1:
+            # every rank must run the same number of mini-batches (one gradient all-reduce each) and roll-outs:
+            # unequal shards (shard_range gives sizes that differ by one when n_global % world != 0) would pair
+            # gradients of different epochs or hang the collective
+            sizes = [None] * self._world
+            dist.all_gather_object(sizes, (int(n_envs), int(n_steps), int(batch_size), int(n_epochs)))
+            if len(set(sizes)) != 1:
+                raise ValueError(f"data-parallel PPO needs identical (n_envs, n_steps, batch_size, n_epochs) on every "
+                                 f"rank, got {sizes}: choose an env count divisible by the world size")
             for p_ in self.policy.parameters():
                 dist.broadcast(p_.data, src=0)
             if seed is not None:

@@ -16,7 +16,13 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "env-steps/sec" and d["unit"] == "env-steps/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 3
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_bench
+    want_kind = "reference" if ref_bench.reference_root() is not None else "port"     # baseline/_ref staged?
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1
+    if want_kind == "reference":      # the unmodified Python PTGEnv ran: its trajectory hash and all three arrangements
+        ref = d["config"]["reference"]
+        assert len(ref["trajectory_sha256"]) == 64 and ref["single_env_steps"] == 5323
+        assert d["value"] == max(ref["subproc_steps_per_s"], ref["dummy6_steps_per_s"], ref["single_env_steps_per_s"])
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 

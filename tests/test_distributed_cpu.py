@@ -93,3 +93,29 @@ def test_data_parallel_ppo_keeps_replicas_identical():
     assert np.array_equal(results[0][0], results[1][0])           # broadcast initial weights
     assert np.array_equal(results[0][1], results[1][1])           # identical after the averaged update
     assert not np.array_equal(results[0][0], results[0][1])       # and the update did move them
+
+
+def _ppo_uneven_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rl_ptg_b200.ppo import PPOCore
+        lo, hi = shard_range(9, rank, world)                      # 5 + 4 envs
+        try:
+            PPOCore(hi - lo, 40, "cpu", n_steps=8, batch_size=16, n_epochs=1, seed=5)
+            ret[rank] = "constructed"
+        except ValueError as e:
+            ret[rank] = str(e)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_ppo_rejects_uneven_shards():
+    """An env count that does not divide by the world size gives ranks different mini-batch counts, i.e. different
+    numbers of gradient all-reduces: refused at construction on every rank instead of hanging later."""
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_ppo_uneven_worker, args=(world, port, ret), nprocs=world, join=True)
+        results = dict(ret)
+    assert all("identical (n_envs" in results[r] for r in range(world)), results

@@ -25,12 +25,16 @@ env.reset_tensor()
 dev = env.device
 g = torch.Generator(device=dev); g.manual_seed(0)
 upool = torch.randint(0, 5, (8, args.envs), generator=g, device=dev, dtype=torch.int64)
+pre = env.rollout_tensor(upool)                      # pre-roll to a stationary plant-state mix (as bench.py does)
+for _ in range(60):
+    env.rollout_tensor(upool, out=pre)
+del pre
 bpe = env.bytes_per_env_step
 tag = os.path.basename(os.environ.get('PTG_B200_SO', 'default'))
 for policy in (["uniform", "sticky"] if args.policy == "both" else [args.policy]):
     # sticky = an agent-like policy: actions change rarely (each env repeats one action)
     pool = upool if policy == "uniform" else upool[:1].repeat(8, 1).contiguous()
-    for t in range(20):
+    for t in range(400):
         env.step_tensor(pool[t % 8])
     torch.cuda.synchronize()
     best = 1e9
