@@ -354,16 +354,23 @@ def run_gpu(args):
     for t in range(P):
         env.step_tensor(pool[t % n_pool])
     barrier()
+    # The K timed steps are bracketed by barrier + synchronize on both sides; LEAD untimed steps are queued in front of
+    # the first event so that the timed launches find a busy GPU and a full launch queue -- otherwise the first timed
+    # kernel waits for its own launch to cross PCIe and runs without the overlap with its predecessor's tail
+    # (programmatic dependent launch), which a 20-step region would not amortise.
+    LEAD = 64
+    for t in range(LEAD):
+        env.step_tensor(pool[(P + t) % n_pool])
     l0 = env.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for t in range(K):
-        env.step_tensor(pool[(P + t) % n_pool])
+        env.step_tensor(pool[(P + LEAD + t) % n_pool])
     ev1.record()
     barrier()
     launches = env.kernel_launches() - l0
     ms = ev0.elapsed_time(ev1)
-    draws_per_step = (total_draws() - draws0) / ((P + K) * n_local)
+    draws_per_step = (total_draws() - draws0) / ((P + LEAD + K) * n_local)
     # secondary action distributions: the load-biased mix, and an agent-like "sticky" policy (each
     # env repeats one action, so almost no transition noise is drawn after warm-up)
     Ks = max(200, K)
@@ -382,6 +389,22 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
+
+    # ---------------- this box's own copy bandwidth (information only; the roofline peak stays MEASURED_PEAKS.json) ----
+    copy_gbs = None
+    if rank == 0:
+        ca = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+        cb = torch.empty_like(ca)
+        best = 1e9
+        for _ in range(6):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            cb.copy_(ca)
+            c1.record()
+            torch.cuda.synchronize()
+            best = min(best, c0.elapsed_time(c1))
+        copy_gbs = 2 * ca.numel() * 4 / (best * 1e-3) / 1e9
+        del ca, cb
 
     # ---------------- rollout kernel (T steps per launch), reported in config ----------------
     T = 16
@@ -477,6 +500,8 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "envs_per_gpu": n_local, "envs_total": n_global,
                        "obs_dim": obs_dim, "noise": "on-device PCG64+ziggurat (numpy-exact)",
                        "preroll_steps": preroll_done, "untimed_single_steps_before_timed_region": P,
+                       "untimed_steps_queued_ahead_of_the_first_event": LEAD,
+                       "copy_gbs_this_box": copy_gbs,
                        "bytes_per_env_step": round(bpe, 2),
                        "bytes_per_env_step_breakdown": {"state_action_obs_reward_done": bpe0,
                                                         "rng_state_per_draw": RNG_BYTES_PER_DRAW,

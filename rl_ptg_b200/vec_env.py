@@ -345,20 +345,15 @@ class PtGVecEnv(_Base):
         # Discrete actions travel as uint8 (the ABI takes PTG_ACT_U8): 1 byte per env over PCIe instead of SB3's int64.
         # Values outside 0..4 map to 255, which the kernel reports like any other invalid action.  torch's converting
         # copy is multi-threaded for large arrays (torch.set_num_threads; under torchrun OMP_NUM_THREADS defaults to 1).
-        if a.flags.c_contiguous and a.dtype in _TORCH_FROM_NUMPY_OK:
-            src = torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
-            if self._act_wire_u8:
-                if self.num_envs <= 4096:
-                    bad = (a < 0) | (a > 4)
-                    if bad.any():
-                        src = torch.from_numpy(np.where(bad, 255, a))
-                    self._act_h.copy_(src)
-                else:
-                    self._act_h.copy_(src.clamp(-1, 5))         # -1 -> 255, 5 stays invalid
-            else:
-                self._act_h.copy_(src)
+        if self._act_wire_u8 and a.dtype != np.uint8:
+            lo, hi = (int(a.min()), int(a.max())) if a.size <= 4096 else \
+                (int(v) for v in torch.aminmax(torch.from_numpy(np.ascontiguousarray(a))))
+            if lo < 0 or hi > 4:                                 # rare: keep the invalid entries visible to the kernel
+                a = np.where((a < 0) | (a > 4), 255, a).astype(np.uint8)
+        if a.flags.c_contiguous and a.flags.writeable and a.dtype in _TORCH_FROM_NUMPY_OK:
+            self._act_h.copy_(torch.from_numpy(a))               # (converting copy: int64 -> uint8)
         else:
-            self._act_h.numpy()[:] = np.where((a < 0) | (a > 4), 255, a) if self._act_wire_u8 else a
+            self._act_h.numpy()[:] = a
         self._act_d.copy_(self._act_h, non_blocking=True)
         _lib.check(self._L.ptg_step(self._h, self._ptr(self._act_d), _TORCH_ACT[self._act_d.dtype],
                                     C.byref(self._io), self._stream()))
