@@ -282,6 +282,39 @@ def strong_scaling_leg(kw, dev, world, rank, peak, draws_per_step, n_total=1 << 
             "episode_length_in_this_leg": 257, "modes": res, "last_record": last}
 
 
+def ppo_quick(kw, dev, n_envs=16384, n_steps=16, n_epochs=2, iters=2):
+    """BASELINE config 5 in one small, time-boxed line (config.ppo of the default bench): the GPU VecEnv feeding the
+    torch policy -- PPO with the reference's hyper-parameters except the roll-out geometry, env + VecNormalize + feature
+    rows + GAE on the device, the policy update in torch (library code: the consumer of the path, not the path)."""
+    import torch
+    from rl_ptg_b200.ppo import PPO, reference_hyper_kwargs
+    from rl_ptg_b200.vec_env import PtGVecEnv
+    hyper = reference_hyper_kwargs()
+    hyper.update(n_steps=n_steps, batch_size=n_envs, n_epochs=n_epochs, seed=3654)
+    env = PtGVecEnv(kw, n_envs, seed=3654, device=dev, obs_layout="flat")
+    model = PPO(env, **hyper)
+    model.learn(n_envs * n_steps)                     # warm-up iteration (cuBLAS, allocator)
+    torch.cuda.synchronize()
+    t0, n0, tc = time.perf_counter(), model.num_timesteps, 0.0
+    for _ in range(iters):
+        c0 = time.perf_counter()
+        model.collect_rollouts()
+        torch.cuda.synchronize()
+        tc += time.perf_counter() - c0
+        model.train()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    steps = model.num_timesteps - n0
+    launches = env.kernel_launches()
+    env.close()
+    return {"workload": "PPO (MultiInputPolicy 2x358 ReLU) on BS2/OP2 mod: env + VecNormalize + feature rows + GAE on the "
+                        "device, policy update in torch fp32", "n_envs": n_envs, "n_steps": n_steps, "batch_size": n_envs,
+            "n_epochs": n_epochs, "iterations_timed": iters, "train_env_steps_per_s": steps / dt,
+            "collect_env_steps_per_s": steps / tc, "collect_share_of_time": tc / dt, "env_kernel_launches": launches,
+            "note": "the reference's shipped TensorBoard run logs time/fps = 166.6 env-steps/s (6 envs, unknown host); "
+                    "`bench.py --workload ppo` is the full-size version of this line"}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -456,6 +489,10 @@ def run_gpu(args):
     if args.strong:
         strong = strong_scaling_leg(kw, dev, world, rank, peak, draws_per_step)
 
+    ppo = None
+    if world == 1 and args.ppo_line:
+        ppo = ppo_quick(kw, dev)
+
     if rank == 0:
         bpe = bpe0 + RNG_BYTES_PER_DRAW * draws_per_step     # + the RNG state of the env-steps that draw noise
         kernel_ms = ms / K                                   # rank 0's own kernel time (CUDA events, same stream)
@@ -523,6 +560,7 @@ def run_gpu(args):
                            "bytes_per_env_step": round(bpe - 64 + 64 / T, 2),     # state stays in registers between steps
                            "roofline_frac": (bpe - 64 + 64 / T) * n_local / (roll_ms * 1e-3) / 1e9 / peak},
                        "strong_scaling": strong,
+                       "ppo": ppo,
                        "host_threads_per_rank": host_threads,
                        "episodes_finished": stats["episodes"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -720,6 +758,8 @@ def main():
     ap.add_argument("--presteps", type=int, default=1024, help="untimed single steps right before the timed region (>= 10 ms)")
     ap.add_argument("--strong", action="store_true", default=True, help="BASELINE config 4 leg: 1M envs in total")
     ap.add_argument("--no-strong", dest="strong", action="store_false")
+    ap.add_argument("--no-ppo-line", dest="ppo_line", action="store_false", default=True,
+                    help="skip config.ppo (BASELINE config 5 as one small time-boxed line)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--e2e-steps", type=int, default=60)

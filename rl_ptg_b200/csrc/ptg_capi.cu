@@ -5,7 +5,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -55,8 +54,6 @@ struct PtgHandle {
     PtgEpisodeStats* d_gather = nullptr;   // all-gather target of ptg_allreduce_stats
     int gather_ranks = 0;
     uint32_t step_serial = 0;
-    int n_sm = 0;                     // SMs of the device (persistent grid = n_sm x resident CTAs per SM of the kernel)
-    int ctas_per_sm_override = 0;     // PTG_CTAS_PER_SM (kernel experiments only)
     int64_t launches = 0;
     double total_steps = 0.0;
 
@@ -84,37 +81,14 @@ namespace {
 
 // Step kernels are launched with programmatic stream serialization (PDL): back-to-back steps overlap the next
 // launch's prologue with the current launch's tail wave (the kernel does griddepcontrol.wait before it reads state).
-// Dynamic shared memory of the step kernels (the state prefetch stages) pushes the CTA past the 48 KB default:
-// opt in once per kernel instantiation and ask for the largest shared-memory carve-out (4 CTAs of ~54 KB per SM).
-cudaError_t configure_step_kernel(const void* kernel, size_t dyn, int* ctas_per_sm) {
-    static std::vector<std::pair<const void*, int>> done;
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    for (const auto& d : done)
-        if (d.first == kernel) { *ctas_per_sm = d.second; return cudaSuccess; }
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    int n = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, PTG_BLOCK, dyn);
-    if (e == cudaSuccess) { done.emplace_back(kernel, std::max(1, n)); *ctas_per_sm = std::max(1, n); }
-    return e;
-}
-
 template <typename K>
 cudaError_t launch_pdl(K kernel, unsigned grid, cudaStream_t st, const DevParams& P, const void* actions, int adtype,
-                       const PtgIO& io, int T, bool many, int n_sm, int ctas_per_sm_override, unsigned block = PTG_BLOCK,
-                       bool no_dyn = false) {
-    const size_t dyn = no_dyn ? 0 : step_dynamic_smem(many);
-    int per_sm = 1;
-    cudaError_t ce = configure_step_kernel(reinterpret_cast<const void*>(kernel), dyn, &per_sm);
-    if (ce != cudaSuccess) return ce;
-    // persistent launches (grid == 0 on entry): one scheduling wave of resident CTAs, tiles b, b + grid, ...
-    if (grid == 0) grid = (unsigned)(n_sm * (ctas_per_sm_override > 0 ? ctas_per_sm_override : per_sm));
+                       const PtgIO& io, int T) {
 #if PTG_PDL
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(block);
-    cfg.dynamicSmemBytes = dyn;
+    cfg.blockDim = dim3(PTG_BLOCK);
+    cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -123,49 +97,30 @@ cudaError_t launch_pdl(K kernel, unsigned grid, cudaStream_t st, const DevParams
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, P, actions, adtype, io, T);
 #else
-    kernel<<<grid, block, dyn, st>>>(P, actions, adtype, io, T);
+    kernel<<<grid, PTG_BLOCK, 0, st>>>(P, actions, adtype, io, T);
     return cudaGetLastError();
 #endif
 }
 
 template <int NV, bool MOD>
 cudaError_t launch_step_t(PtgHandle* h, const void* actions, int adtype, const PtgIO& io, int T, cudaStream_t st) {
-    const unsigned tiles = blocks_for(h->P.n_envs, PTG_BLOCK);
-    // single steps run persistent CTAs (see k_step): grid 0 = "one wave of resident CTAs", capped by the tile count
-    const bool persist = (h->P.flat || PTG_PIPE) && T == 0;
+    unsigned grid = blocks_for(h->P.n_envs, PTG_BLOCK);
+    if (h->P.flat && T == 0)   // single steps of the flat layout: persistent CTAs, one scheduling wave of them (see k_step)
+        grid = std::min<unsigned>(grid, (unsigned)std::max(1, h->P.prefetch_distance / PTG_BLOCK));
     h->P.action_bytes = adtype == PTG_ACT_I64 ? 8 : adtype == PTG_ACT_U8 ? 1 : 4;
     const bool pa13 = NV == 4 && h->P.pa == 13;       // compile-time price_ahead for the reference default
     constexpr int P13 = NV == 4 ? 13 : 0;
-    auto go = [&](auto kernel, int T_, bool many) {
-        unsigned grid = tiles;
-        if (persist) {
-            int per_sm = 1;
-            cudaError_t ce = configure_step_kernel(reinterpret_cast<const void*>(kernel), step_dynamic_smem(many), &per_sm);
-            if (ce != cudaSuccess) return ce;
-            grid = std::min<unsigned>(tiles, (unsigned)(h->n_sm * (h->ctas_per_sm_override > 0 ? h->ctas_per_sm_override : per_sm)));
-        }
-        return launch_pdl(kernel, grid, st, h->P, actions, adtype, io, T_, many, h->n_sm, h->ctas_per_sm_override);
-    };
     if (h->P.flat) {                                  // (validated at create: price_ahead == 13, train mode)
-        if (T > 0) return go(k_step<4, MOD, true, false, 13, true>, T, true);
-        return go(k_step<4, MOD, false, false, 13, true>, 1, false);
+        if (T > 0) return launch_pdl(k_step<4, MOD, true, false, 13, true>, grid, st, h->P, actions, adtype, io, T);
+        return launch_pdl(k_step<4, MOD, false, false, 13, true>, grid, st, h->P, actions, adtype, io, 1);
     } else if (T > 0) {
-        if (pa13) return go(k_step<NV, MOD, true, false, P13>, T, true);
-        return go(k_step<NV, MOD, true, false, 0>, T, true);
+        if (pa13) return launch_pdl(k_step<NV, MOD, true, false, P13>, grid, st, h->P, actions, adtype, io, T);
+        return launch_pdl(k_step<NV, MOD, true, false, 0>, grid, st, h->P, actions, adtype, io, T);
     } else if (h->P.eval_mode && io.info) {
-        return go(k_step<NV, MOD, false, true, 0>, 1, false);
+        return launch_pdl(k_step<NV, MOD, false, true, 0>, grid, st, h->P, actions, adtype, io, 1);
     }
-#if PTG_WS
-    {   // the warp-specialised kernel: one tile per CTA, eight plant warps + the window warps
-        auto ws = [&](auto kernel) {
-            return launch_pdl(kernel, tiles, st, h->P, actions, adtype, io, 1, false, h->n_sm, 0, PTG_WS_THREADS, true);
-        };
-        if (pa13) return ws(k_step_ws<NV, MOD, P13>);
-        return ws(k_step_ws<NV, MOD, 0>);
-    }
-#endif
-    if (pa13) return go(k_step<NV, MOD, false, false, P13>, 1, false);
-    return go(k_step<NV, MOD, false, false, 0>, 1, false);
+    if (pa13) return launch_pdl(k_step<NV, MOD, false, false, P13>, grid, st, h->P, actions, adtype, io, 1);
+    return launch_pdl(k_step<NV, MOD, false, false, 0>, grid, st, h->P, actions, adtype, io, 1);
 }
 template <int NV, bool MOD>
 cudaError_t launch_reset_t(PtgHandle* h, const int64_t* seeds, const uint8_t* mask, const PtgIO& io, cudaStream_t st) {
@@ -499,8 +454,6 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
         double waves = 1.0;                       // PTG_PREFETCH_WAVES: kernel experiments only
         if (const char* w = getenv("PTG_PREFETCH_WAVES")) waves = atof(w);
         P.prefetch_distance = (int32_t)(waves * prop.multiProcessorCount * PTG_STEP_MIN_BLOCKS) * PTG_BLOCK;
-        h->n_sm = prop.multiProcessorCount;
-        if (const char* w = getenv("PTG_CTAS_PER_SM")) h->ctas_per_sm_override = std::max(1, atoi(w));
     }
     k_construct<<<blocks_for(n_envs, 256), 256>>>(P);
     h->launches += 1;

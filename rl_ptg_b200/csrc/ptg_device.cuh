@@ -130,9 +130,6 @@ static_assert(sizeof(RngRec) == 32, "RngRec layout");
 #ifndef PTG_L2_HINTS
 #define PTG_L2_HINTS 1
 #endif
-#ifndef PTG_STREAM_HINT
-#define PTG_STREAM_HINT 1        // streaming stores / bulk stores carry evict_first (0: default policy; kernel experiments)
-#endif
 #define PTG_L2_EVICT_FIRST 0x12F0000000000000ull
 #define PTG_L2_EVICT_LAST 0x14F0000000000000ull
 struct U256 { unsigned long long a, b, c, d; };
@@ -158,7 +155,7 @@ __device__ __forceinline__ int ldg32_nc_keep(const int* p) {     // small read-o
 // streaming stores (written once per step, re-read one full step later at the earliest)
 template <typename T>
 __device__ __forceinline__ void st_stream(T* p, T v) {
-#if PTG_L2_HINTS && PTG_STREAM_HINT
+#if PTG_L2_HINTS
     __stcs(p, v);
 #else
     *p = v;

@@ -16,10 +16,6 @@
 
 #include "ptg_device.cuh"
 
-#ifndef PTG_DIAG
-#define PTG_DIAG 0               // 1..4: diagnostic builds that drop parts of the step (kernel experiments only, results invalid)
-#endif
-
 // ------------------------------------------------------------------------------------------------------------
 // table construction
 // ------------------------------------------------------------------------------------------------------------
@@ -224,7 +220,7 @@ struct ObsRegs {            // what one env contributes to the observation, in r
 // --- TMA (bulk async copy) helpers: shared::cta -> global, 1-D ---------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
-#if PTG_L2_HINTS && PTG_STREAM_HINT
+#if PTG_L2_HINTS
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
                  ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes), "l"(PTG_L2_EVICT_FIRST) : "memory");
 #else
@@ -243,13 +239,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // ([32][pa] floats, stride pa: conflict free for odd pa) and leave the SM as ONE bulk async copy (TMA) per block
 // and warp -- 128*pa contiguous bytes -- issued by lane 0; the nine scalar keys are plain coalesced stores.
 // PAC > 0 fixes price_ahead at compile time (the reference default 13) so the staging stores need no predicates.
-__device__ __forceinline__ void tma_store_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-
-template <int NV, bool MOD, int PAC, bool DOUBLE_BUFFERED = false>
+template <int NV, bool MOD, int PAC>
 __device__ __forceinline__ void stage_windows(const DevParams& P, float* sm, int lane, const float4 (&hrow)[NV]) {
     const int pa = PAC > 0 ? PAC : P.pa;
-    // previous bulk stores are done with sm (DOUBLE_BUFFERED: all but the latest group, which reads the other buffer)
-    if (lane == 0) { if (DOUBLE_BUFFERED) tma_store_wait_read_1(); else tma_store_wait_read(); }
+    if (lane == 0) tma_store_wait_read();         // previous step's bulk stores (rollout kernel) are done with sm
     __syncwarp();
     float w[4 * NV];
 #pragma unroll
@@ -277,11 +270,7 @@ __device__ __forceinline__ void issue_window_stores(const DevParams& P, float* _
     float* smB = sm + PTG_STAGE_FLOATS(NV);
     float* gA = obs + P.off_win0 + warp_env0 * pa;
     float* gB = obs + P.off_win1 + warp_env0 * pa;
-#if PTG_DIAG == 3
-    __syncwarp();
-    return;
-#endif
-    if (nvalid == 32 && PTG_DIAG != 4) {
+    if (nvalid == 32) {
         fence_proxy_async_smem();                 // make the generic-proxy writes visible to the async proxy
         __syncwarp();
         if (lane == 0) {
@@ -653,10 +642,6 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
 #ifndef PTG_PDL
 #define PTG_PDL 1
 #endif
-#ifndef PTG_LATE_ROWS
-#define PTG_LATE_ROWS 1
-#endif
-
 #ifndef PTG_STEP_MIN_BLOCKS
 #define PTG_STEP_MIN_BLOCKS 4        // CTAs of 256 threads per SM the step kernel is compiled for (<= 64 registers)
 #endif
@@ -668,8 +653,9 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
 #define PTG_STATE_L2 1
 #endif
 #ifndef PTG_PREFETCH_STATE
-#define PTG_PREFETCH_STATE 1     // prefetch.global.L2 of the plant state of the CTA one scheduling wave later
-#endif
+#define PTG_PREFETCH_STATE 0     // 1: prefetch.global.L2 of the plant state of the CTA one scheduling wave later (the
+#endif                           //    round-1 arrangement for streamed state; pointless once the state lives in L2, and
+                                 //    its address arithmetic cost the roll-out kernel two spilled registers: 34.8 -> 33.4 us)
 #if PTG_STATE_L2 && PTG_L2_HINTS
 #define PTG_LD_STATE(p) ld_keep(p)
 #define PTG_ST_STATE(p, v) st_keep(p, v)
@@ -731,15 +717,7 @@ __device__ __forceinline__ void gather_step_entry(const DevParams& P, int ent, i
 //      plant transition: covers the latency of 1.)
 //   3. plant transition (may draw noise) -> step-table entry gather -> reward, scalars
 //   4. bulk stores
-#define PTG_WS_WINDOW_WARPS 2      // warp-specialised step kernel: window warps per CTA (each serves 4 plant warps)
-#define PTG_WS_THREADS (PTG_BLOCK + 32 * PTG_WS_WINDOW_WARPS)
-// named barrier 1 of the warp-specialised kernel: "the window warps have read (k, act_ep_h, ep_count) of this tile"
-__device__ __forceinline__ void ws_barrier_sync() { asm volatile("barrier.sync 1, %0;" ::"n"(PTG_WS_THREADS) : "memory"); }
-__device__ __forceinline__ void ws_barrier_arrive() { asm volatile("barrier.arrive 1, %0;" ::"n"(PTG_WS_THREADS) : "memory"); }
-
-// WS = true: the plant half of the warp-specialised kernel (k_step_ws) -- the market windows are produced by the
-// CTA's window warps, this thread only fetches the electricity price of the new hour.
-template <int NV, bool MOD, bool EVAL, int PAC, bool WS = false>
+template <int NV, bool MOD, bool EVAL, int PAC>
 __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, long long action_raw, int adtype,
                                          bool single, int e, bool active, int lane, int warp_env0,
                                          int nvalid, float* sm, const uint64_t* zig_kiwi, float* __restrict__ obs_out,
@@ -752,7 +730,6 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
     int t_hour_out = 0;
     // termination only depends on the step counter (:508-511, k before the increment): known up front, so the
     // common case (no env of the warp ends its episode) can hand its window tiles to the TMA early
-    constexpr bool NOWIN = WS || PTG_DIAG == 1;       // no window work in this thread
     const int done = active && (k == P.eps_sim_steps - 6);
     const bool any_done = __any_sync(0xffffffffu, done);
     bool win_moved = false;
@@ -777,50 +754,21 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         // the market-window blocks of the observation only move when the clock crosses an hour (or the episode ends)
         win_moved = done || (sec / 3600u) != ((sec - (unsigned)P.sim_step) / 3600u);
         clamp_market_index(P, t_hour, t_day);
+        load_hour_row<NV>(P, t_hour, hrow);
+        day = load_day_row(P, t_day);
         int k1 = k + 1;
         PTG_CHECK_INDEX(P, k1, P.eps_sim_steps + 1, 5);
-        double el;
-        if (NOWIN) {      // only the electricity price of the new hour (the last 8 bytes of its row)
-            el = __ldg(reinterpret_cast<const double*>(reinterpret_cast<const float*>(P.hour_tab + (int64_t)t_hour * NV) + 4 * NV - 2));
-        } else {
-#if PTG_DIAG == 5
-#pragma unroll
-            for (int v = 0; v < NV; ++v) hrow[v] = make_float4((float)t_hour, 0.f, 0.f, 0.f);
-#else
-            load_hour_row<NV>(P, t_hour, hrow);
-#endif
-        }
-#if !PTG_LATE_ROWS
-        day = load_day_row(P, t_day);
         const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
-#endif
-        if (!NOWIN) {
-            stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
-            el = hour_row_el<NV>(hrow);               // from here on the hour row is dead (registers!)
-            // the window tiles go to the TMA before the transition: the fence in front of a bulk store waits for the
-            // thread's outstanding accesses, so it must not sit behind the RNG / step-table requests
-            if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
-        }
+        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
+        const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
+        // the window tiles go to the TMA before the transition: the fence in front of a bulk store waits for the
+        // thread's outstanding accesses, so it must not sit behind the RNG / step-table requests
+        if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
         // (3) plant transition (requests the RNG record when it draws) -> step-table entry (2 x 32 B sectors)
-#if PTG_DIAG >= 2      // (diagnostic build, results invalid: the window path alone -- no transition, no step-table gather)
-        const int ent = 0; const int state_change = 0; (void)prev_state; (void)lut_val; (void)draws;
-        U256 qc = {0, 0, 0, 0}, qn = {0, 0, 0, (unsigned long long)(uint32_t)tinfo};
-        k1 = k + 1;
-#else
         const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep);
         const int state_change = (prev_state != (int)(meta & 7));
         U256 qc, qn;      // qc = {c_gas, c_eua, c_el, c_0}, qn = {norm[6], tinfo, pad}
         gather_step_entry(P, ent, lane, nvalid, qc, qn);
-#endif
-#if PTG_DIAG == 5
-        day = DayRow{(double)t_day, 1.0, 0.f, 0.f, 0.f, 0.f};
-        const float2 sc2 = make_float2((float)k1, 0.f);
-#elif PTG_LATE_ROWS
-        // the day row and the clock row are only needed from here on: requested together with the step-table entry
-        // (L1-resident rows), so their registers are not live across the transition / noise draw
-        day = load_day_row(P, t_day);
-        const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
-#endif
         // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
         const double c_gas = __longlong_as_double((long long)qc.a), c_eua = __longlong_as_double((long long)qc.b);
         const double c_el = __longlong_as_double((long long)qc.c), c_0 = __longlong_as_double((long long)qc.d);
@@ -840,7 +788,6 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
             write_info<NV>(P, io.info, e, InfoKey{k, t_hour, t_day, ent, state_change, meta, rew,
                                                   ep_ret + (double)nchg * P.penalty});
         k += 1;
-        if (WS) ws_barrier_sync();                    // the window warps have read this tile's (k, act_ep_h, ep_count)
         if (done) finish_episode<NV, MOD>(P, io, e, single, k, ep_ret, (meta >> 4) & 7,
                                           ObsKey{ent, t_hour, t_day, (int)(meta & 7), k}, draws_ep);
         if (done && P.auto_reset) {                   // SB3 auto-reset (DummyVecEnv.step_wait), out of line
@@ -861,15 +808,12 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         for (int v = 0; v < NV; ++v) hrow[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         day = DayRow{};
         o = ObsRegs{};
-        if (WS) ws_barrier_sync();
-        if (!NOWIN) {
-            stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
-            if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
-        }
+        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
+        if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
     }
     // episode ends are rare: only then is the warp's window tile staged again, from re-read hour rows (the reset
     // observation of the done lanes, the unchanged rows of the others), and stored after the fact
-    if (any_done && !NOWIN) {
+    if (any_done) {
         float4 h2[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) h2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -882,53 +826,8 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         st_stream(rew_out + e, reward);
         st_stream(done_out + e, (uint8_t)done);
     }
-    if (!WS && single && io.windows_changed != nullptr && __any_sync(0xffffffffu, win_moved) && lane == 0)
+    if (single && io.windows_changed != nullptr && __any_sync(0xffffffffu, win_moved) && lane == 0)
         *io.windows_changed = P.step_serial;        // (same value from every warp: plain store, no atomic needed)
-}
-
-// The window half of the warp-specialised step kernel: one warp produces the market-window blocks (Pot_Reward /
-// Part_Full, or Elec_Price) of four 32-env groups of its CTA's tile.  Everything it needs is a pure function of the
-// env's state BEFORE the step -- the step counter, the episode's first hour and, when the episode ends in this step,
-// the schedule position of the next one -- so it runs concurrently with the plant warps and only has to read those
-// words before they overwrite them (named barrier 1).  104 of the 140 observation bytes of an env-step leave the SM
-// from here: hour row (L1 / L2 gather) -> transposed in shared memory -> one bulk store (TMA) per block and group.
-template <int NV, bool MOD, int PAC>
-__device__ __forceinline__ void window_role(const DevParams& P, const PtgIO& io, float* __restrict__ obs_out,
-                                            int tile_env0, int n_envs, int ww, int lane, float* sm2) {
-    constexpr int G = 8 / PTG_WS_WINDOW_WARPS;        // 32-env groups per window warp
-    int t_hour[G];
-    bool moved = false;
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const int e = tile_env0 + (ww * G + g) * 32 + lane;
-        const int le = e < n_envs ? e : n_envs - 1;
-        const int k = __ldcv(reinterpret_cast<const int*>(P.core + le) + 2);
-        int ep_h = __ldcv(reinterpret_cast<const int*>(P.ep + le));
-        const bool done = k == P.eps_sim_steps - 6;
-        unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
-        if (done && P.auto_reset) {                   // the returned observation is the next episode's reset observation
-            int ep_d;
-            episode_offsets(P, le, P.ep_count[le] + 1, ep_h, ep_d);
-            sec = 0;
-        }
-        t_hour[g] = ep_h + (int)(sec / 3600u);
-        moved |= done || (sec / 3600u) != ((sec - (unsigned)P.sim_step) / 3600u);
-    }
-    ws_barrier_arrive();                              // the plant warps may overwrite the state from here on
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        const int warp_env0 = tile_env0 + (ww * G + g) * 32;
-        if (warp_env0 >= n_envs) break;
-        int th = t_hour[g], td = 0;
-        clamp_market_index(P, th, td);
-        float4 hrow[NV];
-        load_hour_row<NV>(P, th, hrow);
-        float* sm = sm2 + (g & 1) * 2 * PTG_STAGE_FLOATS(NV);
-        stage_windows<NV, MOD, PAC, true>(P, sm, lane, hrow);
-        issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, min(32, n_envs - warp_env0));
-    }
-    if (io.windows_changed != nullptr && __any_sync(0xffffffffu, moved) && lane == 0) *io.windows_changed = P.step_serial;
-    if (lane == 0) tma_store_wait_read();             // the staging buffers must outlive the bulk stores' reads
 }
 
 // One env step with the flat observation layout: the same transition / reward path as step_one, but the whole
@@ -1023,45 +922,6 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
     }
 }
 
-// --- per-thread asynchronous global -> shared copies (LDGSTS): every thread stages ITS OWN state words of the next
-//     tile into its own shared-memory slots while it works on the current tile; no register is tied up by the loads in
-//     flight and no cross-thread synchronisation is needed (a thread only reads back what it copied itself) ---
-#ifndef PTG_PIPE
-#define PTG_PIPE 1               // single-step kernels: persistent CTAs + double-buffered state prefetch
-#endif
-template <int BYTES>
-__device__ __forceinline__ void cp_async_keep(void* sdst, const void* gsrc) {
-#if PTG_STATE_L2 && PTG_L2_HINTS
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], %2, %3;"
-                 ::"r"(smem_u32(sdst)), "l"(gsrc), "n"(BYTES), "l"(PTG_L2_EVICT_LAST) : "memory");
-#else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(sdst)), "l"(gsrc), "n"(BYTES) : "memory");
-#endif
-}
-template <int BYTES>
-__device__ __forceinline__ void cp_async_stream(void* sdst, const void* gsrc) {
-#if PTG_L2_HINTS
-    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], %2, %3;"
-                 ::"r"(smem_u32(sdst)), "l"(gsrc), "n"(BYTES), "l"(PTG_L2_EVICT_FIRST) : "memory");
-#else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(sdst)), "l"(gsrc), "n"(BYTES) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// The per-thread state slots of one prefetch stage (structure of arrays: conflict-free LDS of each word size).
-struct StateStage {
-    int4 core[PTG_BLOCK];
-    double ep_ret[PTG_BLOCK];
-    int2 ep[PTG_BLOCK];
-    long long act[PTG_BLOCK];      // raw action word (I64: 8 B, I32 / F32: the low 4 B; U8 actions are loaded directly)
-    int32_t tinfo[PTG_BLOCK];
-};
-
-__host__ __device__ constexpr size_t step_dynamic_smem(bool many) { return (PTG_PIPE && !many) ? 2 * sizeof(StateStage) : 0; }
-
 // VecEnv.step_wait(): MANY = false -> exactly one step (ptg_step); MANY = true -> T steps with the plant state
 // kept in registers between steps (ptg_step_many).  EVAL = the 24-field info of train_or_eval == "eval".
 template <int NV, bool MOD, bool MANY, bool EVAL, int PAC, bool FLAT = false>
@@ -1095,32 +955,9 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     // own next tile): its single end-of-step bulk store would otherwise hold the CTA's slot for ~10 % of its lifetime
     // while the TMA reads the tile; with a next tile to work on, that wait disappears (63.7 -> 58.1 us).  The
     // key-major layout hands its tiles to the TMA early and is faster with one tile per CTA (54 vs 56.5 us).
-    // PTG_PIPE (single-step kernels): the CTA is persistent and every thread keeps the state words of its NEXT tile in
-    // flight as asynchronous global -> shared copies (cp.async, two stages) while it works on the current tile, so a
-    // tile starts from shared memory instead of waiting for an L2 / DRAM round trip (17 % of the warp stall samples
-    // of the one-tile-per-CTA kernel sat on those loads).
-    constexpr bool PIPE = PTG_PIPE && !MANY;
-    constexpr bool PERSIST = (FLAT || PIPE) && !MANY;   // (the roll-out kernel's stores overlap its next step anyway)
-    extern __shared__ __align__(16) unsigned char ptg_dyn_smem[];      // PIPE: 2 x StateStage (see step_dynamic_smem)
-    StateStage* const st_stage = reinterpret_cast<StateStage*>(ptg_dyn_smem);
-    auto issue_state = [&](int tile_, int slot) {       // this thread's five state words of tile_ -> stage `slot`
-        const int e_ = tile_ * PTG_BLOCK + (int)threadIdx.x;
-        if (tile_ * PTG_BLOCK < n_envs) {
-            const int le_ = e_ < n_envs ? e_ : n_envs - 1;
-            StateStage& S = st_stage[slot];
-            cp_async_keep<16>(&S.core[threadIdx.x], P.core + le_);
-            cp_async_keep<8>(&S.ep_ret[threadIdx.x], P.ep_ret + le_);
-            cp_async_keep<8>(&S.ep[threadIdx.x], P.ep + le_);
-            cp_async_keep<4>(&S.tinfo[threadIdx.x], P.tinfo + le_);
-            if (adtype == PTG_ACT_I64) cp_async_stream<8>(&S.act[threadIdx.x], (const long long*)actions + le_);
-            else if (adtype != PTG_ACT_U8) cp_async_stream<4>(&S.act[threadIdx.x], (const int*)actions + le_);
-        }
-        cp_async_commit();                              // (an empty group when the tile is out of range)
-    };
-    if (PIPE) issue_state((int)blockIdx.x, 0);
+    constexpr bool PERSIST = FLAT && !MANY;             // (the roll-out kernel's stores overlap its next step anyway)
     if (PERSIST && use_zig) __syncthreads();            // ziggurat table visible to every warp of the CTA
-    int pipe_it = 0;
-    for (int tile = blockIdx.x; tile * PTG_BLOCK < n_envs; tile += gridDim.x, ++pipe_it) {
+    for (int tile = blockIdx.x; tile * PTG_BLOCK < n_envs; tile += gridDim.x) {
     const int e = tile * PTG_BLOCK + (int)threadIdx.x;
     const int warp_env0 = e - lane;
     const bool warp_in_range = warp_env0 < n_envs;
@@ -1128,28 +965,17 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     const bool active = e < n_envs;
     const int le = active ? e : n_envs - 1;             // tail lanes shadow the last env (no stores)
 
-    int4 core; int32_t tinfo; int2 ep; double ep_ret; long long action_raw;
-    if (PIPE) {
-        issue_state(tile + (int)gridDim.x, (pipe_it + 1) & 1);      // next tile: in flight during this one
-        cp_async_wait<1>();                                          // this tile's words have landed
-        const StateStage& S = st_stage[pipe_it & 1];
-        core = S.core[threadIdx.x]; tinfo = S.tinfo[threadIdx.x]; ep = S.ep[threadIdx.x]; ep_ret = S.ep_ret[threadIdx.x];
-        if (adtype == PTG_ACT_I64) action_raw = S.act[threadIdx.x];
-        else if (adtype == PTG_ACT_U8) action_raw = load_action_raw(actions, adtype, le);
-        else action_raw = (long long)*reinterpret_cast<const int*>(&S.act[threadIdx.x]);
-    } else {
-        core = PTG_LD_STATE(P.core + le);
-        tinfo = PTG_LD_STATE(P.tinfo + le);
-        ep = PTG_LD_STATE(P.ep + le);
-        ep_ret = PTG_LD_STATE(P.ep_ret + le);
-        action_raw = load_action_raw(actions, adtype, le);
-    }
+    const int4 core = PTG_LD_STATE(P.core + le);
+    int32_t tinfo = PTG_LD_STATE(P.tinfo + le);
+    int2 ep = PTG_LD_STATE(P.ep + le);
+    double ep_ret = PTG_LD_STATE(P.ep_ret + le);
+    long long action_raw = load_action_raw(actions, adtype, le);
     if (!PERSIST && use_zig) __syncthreads();           // (one tile per CTA: the barrier sits behind the state loads)
     if (!warp_in_range) continue;                       // whole warp out of range
     int i = core.x, j = core.y, k = core.z;
     uint32_t meta = (uint32_t)core.w;
 #if PTG_PREFETCH_STATE
-    if (!PIPE) {   // pull the plant state of the CTA that will run one scheduling wave later into L2 (fire and forget)
+    {   // pull the plant state of the CTA that will run one scheduling wave later into L2 (fire and forget)
         const int pe = e + P.prefetch_distance;
         if (pe < n_envs) {
             prefetch_l2(P.core + pe);
@@ -1187,63 +1013,6 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     }
     }
     if (lane == 0) tma_store_wait_read();               // the staging buffer must outlive the bulk stores' reads
-}
-
-// Warp-specialised single step (key-major layout, train mode): a CTA is eight PLANT warps (one env per thread: state
-// machine, noise, step-table gather, reward, scalar observation blocks, state write-back) plus PTG_WS_WINDOW_WARPS
-// WINDOW warps (see window_role).  The two halves of a step are independent, so the window stream -- half of all the
-// bytes of a step -- keeps the memory system busy while the plant warps sit in their dependent gather chain, and the
-// plant threads no longer carry the hour row (16 registers) through the transition.
-#ifndef PTG_WS
-#define PTG_WS 1                 // ptg_step (key-major layout, train mode) runs the warp-specialised kernel
-#endif
-#ifndef PTG_WS_MIN_BLOCKS
-#define PTG_WS_MIN_BLOCKS 4
-#endif
-template <int NV, bool MOD, int PAC>
-__global__ void __launch_bounds__(PTG_WS_THREADS, PTG_WS_MIN_BLOCKS)
-k_step_ws(const __grid_constant__ DevParams P, const void* __restrict__ actions, int adtype,
-          const __grid_constant__ PtgIO io, int T) {
-    __shared__ __align__(128) float stage[PTG_WS_WINDOW_WARPS][2][2 * PTG_STAGE_FLOATS(NV)];
-    __shared__ __align__(16) uint64_t zig_kiwi[2 * 256];
-    const int n_envs = (int)P.n_envs;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const bool use_zig = P.noise_mode == PTG_NOISE_NUMPY;
-#if PTG_PDL
-    asm volatile("griddepcontrol.launch_dependents;");
-#endif
-    if (use_zig && threadIdx.x < 256) {
-        zig_kiwi[2 * threadIdx.x] = __ldg(P.zig.ki + threadIdx.x);
-        zig_kiwi[2 * threadIdx.x + 1] = (uint64_t)__double_as_longlong(__ldg(P.zig.wi + threadIdx.x));
-    }
-#if PTG_PDL
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-    const int tile_env0 = (int)blockIdx.x * PTG_BLOCK;
-    if (wid >= PTG_BLOCK / 32) {
-        window_role<NV, MOD, PAC>(P, io, io.obs, tile_env0, n_envs, wid - PTG_BLOCK / 32, lane, &stage[wid - PTG_BLOCK / 32][0][0]);
-        return;
-    }
-    const int e = tile_env0 + (int)threadIdx.x;
-    const int warp_env0 = e - lane;
-    const int nvalid = min(32, n_envs - warp_env0);
-    const bool active = e < n_envs;
-    const int le = active ? e : n_envs - 1;
-    const int4 core = PTG_LD_STATE(P.core + le);
-    int32_t tinfo = PTG_LD_STATE(P.tinfo + le);
-    int2 ep = PTG_LD_STATE(P.ep + le);
-    double ep_ret = PTG_LD_STATE(P.ep_ret + le);
-    const long long action_raw = load_action_raw(actions, adtype, le);
-    if (use_zig) asm volatile("barrier.sync 2, %0;" ::"n"(PTG_BLOCK) : "memory");      // plant warps only: table staged
-    int i = core.x, j = core.y, k = core.z;
-    uint32_t meta = (uint32_t)core.w;
-    step_one<NV, MOD, false, PAC, true>(P, io, action_raw, adtype, true, e, active, lane, warp_env0, max(nvalid, 0), nullptr,
-                                        use_zig ? zig_kiwi : nullptr, io.obs, io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
-    if (active) {
-        PTG_ST_STATE(P.core + e, make_int4(i, j, k, (int)meta));
-        PTG_ST_STATE(P.tinfo + e, tinfo);
-        PTG_ST_STATE(P.ep_ret + e, ep_ret);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
