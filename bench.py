@@ -251,7 +251,7 @@ def strong_scaling_leg(kw, dev, world, rank, peak, draws_per_step, n_total=1 << 
     for name, issue, bpe in modes:
         for _ in range(2):                              # warm-up roll-outs (and a first use of the communicator)
             issue()
-            env.episode_stats_async(clear=True)
+            env.episode_stats_async(clear=True, overlap=True)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -259,8 +259,12 @@ def strong_scaling_leg(kw, dev, world, rank, peak, draws_per_step, n_total=1 << 
         e0.record()
         for r in range(rollouts):
             issue()
-            rec = env.episode_stats_async(clear=True)   # device reduction + NCCL all-gather + combine, in stream
-            stats_h[r].copy_(rec, non_blocking=True)
+            # local reduction in stream; the NCCL all-gather + combine on the env's side stream, under the next roll-out
+            rec = env.episode_stats_async(clear=True, overlap=True)
+            with torch.cuda.stream(env.stats_stream or torch.cuda.current_stream(dev)):
+                stats_h[r].copy_(rec, non_blocking=True)
+        if env.stats_stream is not None:
+            torch.cuda.current_stream(dev).wait_stream(env.stats_stream)     # the last collective is inside the region
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -276,8 +280,9 @@ def strong_scaling_leg(kw, dev, world, rank, peak, draws_per_step, n_total=1 << 
     last = stats_dict(stats_h[-1].numpy(), world)
     env.close()
     return {"envs_total": n_total, "envs_per_gpu": n, "T": T, "rollouts_timed": rollouts,
-            "collective": "ptg_episode_stats + ptg_allreduce_stats (ncclAllGather of 64 B + combine kernel) once per "
-                          "roll-out inside the timed loop" if world > 1 else
+            "collective": "ptg_episode_stats (in stream) + ptg_allreduce_stats (ncclAllGather of 64 B + combine kernel, on "
+                          "a side stream so that it overlaps the next roll-out) once per roll-out inside the timed loop; "
+                          "the region ends after the last collective" if world > 1 else
                           "ptg_episode_stats once per roll-out inside the timed loop (one rank: nothing to gather)",
             "episode_length_in_this_leg": 257, "modes": res, "last_record": last}
 

@@ -190,7 +190,9 @@ class PtGVecEnv(_Base):
         self._info = torch.zeros((_abi.PTG_N_INFO, n), dtype=torch.float64, device=dev)
         self._ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
         self._ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
-        self._stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._stats_bufs = [torch.zeros(8, dtype=torch.float64, device=dev) for _ in range(2)]
+        self._stats, self._stats_flip, self._stats_done, self._stats_ranks = self._stats_bufs[0], 0, [None, None], 1
+        self.stats_stream = None                 # side stream of episode_stats_async(overlap=True), created on first use
         self._win_flag = torch.zeros(1, dtype=torch.int32, device=dev)     # PtgIO.windows_changed (step serial stamp)
         self._obs_dict = self._obs_views(self._obs)          # views are created once; buffers are reused
         self._io = self._make_io(self._obs, self._reward, self._done, self._term_obs,
@@ -627,20 +629,43 @@ class PtGVecEnv(_Base):
             self._comm = comm
         return self._comm
 
-    def episode_stats_async(self, clear: bool = True, reduce: bool = True) -> torch.Tensor:
+    def episode_stats_async(self, clear: bool = True, reduce: bool = True, overlap: bool = False) -> torch.Tensor:
         """Device-side part of ``episode_stats``: the reduction over this rank's envs and -- with NCCL initialised --
-        the cross-rank all-gather + combine inside the library (``ptg_allreduce_stats``), all on the current stream
-        without a host synchronisation.  Returns the 8 x fp64 ``PtgEpisodeStats`` record (device tensor, reused)."""
+        the cross-rank all-gather + combine inside the library (``ptg_allreduce_stats``), without a host
+        synchronisation.  Returns the 8 x fp64 ``PtgEpisodeStats`` record (device tensor, one of two reused buffers).
+
+        ``overlap=False``: everything on the current stream.  ``overlap=True``: only the local reduction (which reads
+        and clears the per-env accumulators) stays on the current stream; the latency-bound NCCL all-gather + combine go
+        to ``self.stats_stream`` and overlap the next roll-out -- the record is then ordered on that stream (read it
+        under ``torch.cuda.stream(env.stats_stream)`` or after a device synchronisation)."""
         import torch.distributed as dist
         self._check_open()
-        _lib.check(self._L.ptg_episode_stats(self._h, self._ptr(self._stats), int(clear), self._stream()))
+        idx = self._stats_flip
+        self._stats_flip ^= 1
+        rec = self._stats_bufs[idx]
+        main = torch.cuda.current_stream(self.device)
+        if self._stats_done[idx] is not None:
+            main.wait_event(self._stats_done[idx])      # the side stream's last use of this buffer (two calls ago)
+            self._stats_done[idx] = None
+        _lib.check(self._L.ptg_episode_stats(self._h, self._ptr(rec), int(clear), C.c_void_p(main.cuda_stream)))
         if (reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
                 and dist.get_backend() == "nccl"):
-            _lib.check(self._L.ptg_allreduce_stats(self._h, self._nccl_comm(), self._ptr(self._stats), self._stream()))
+            st = main
+            if overlap:
+                if self.stats_stream is None:
+                    self.stats_stream = torch.cuda.Stream(device=self.device)
+                st = self.stats_stream
+                st.wait_stream(main)
+            _lib.check(self._L.ptg_allreduce_stats(self._h, self._nccl_comm(), self._ptr(rec), C.c_void_p(st.cuda_stream)))
+            if overlap:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self._stats_done[idx] = ev
             self._stats_ranks = dist.get_world_size()
         else:
             self._stats_ranks = 1
-        return self._stats
+        self._stats = rec
+        return rec
 
     def episode_stats(self, clear: bool = True, reduce: bool = True) -> dict:
         """Finished-episode statistics since the last clear: device reduction (warp shuffles, deterministic), then --

@@ -41,8 +41,19 @@ all_recs = [torch.empty_like(rec) for _ in range(world)]
 dist.all_gather(all_recs, rec)
 same = all(torch.equal(all_recs[0], r) for r in all_recs)
 ok = same and got == want and got["episodes"] == n_global * (steps // 25) and got["env_steps"] == n_global * steps
+# the overlapped form: local reduction in stream, all-gather + combine on the env's side stream, two records in flight
+for t in range(50):
+    env.step_tensor(torch.randint(0, 5, (hi - lo,), generator=g, device=dev))
+r1 = env.episode_stats_async(clear=True, overlap=True)
+for t in range(25):
+    env.step_tensor(torch.randint(0, 5, (hi - lo,), generator=g, device=dev))
+r2 = env.episode_stats_async(clear=True, overlap=True)
+torch.cuda.synchronize()
+d1, d2 = stats_dict(r1.cpu().numpy(), world), stats_dict(r2.cpu().numpy(), world)
+ok = ok and d1["episodes"] == n_global * 2 and d1["env_steps"] == n_global * 50 \
+    and d2["episodes"] == n_global and d2["env_steps"] == n_global * 25 and d1["ranks"] == world
 if rank == 0:
-    print(f"ptg_allreduce_stats on {world} GPUs: {'OK' if ok else 'MISMATCH'} {got}")
+    print(f"ptg_allreduce_stats on {world} GPUs: {'OK' if ok else 'MISMATCH'} {got} overlapped: {d1['episodes']} / {d2['episodes']} episodes")
 env.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -1,6 +1,6 @@
 """Turn gpurun_out/ ncu artefacts into the tracked summaries under profiles/.
 
-    python tools/summarize_profile.py <round tag> <launches.csv> <full.ncu-rep>
+    python tools/summarize_profile.py <round tag> <launches.csv> <full.ncu-rep> ["<command the launch list was taken over>"]
 """
 import collections
 import csv
@@ -10,6 +10,7 @@ import subprocess
 import sys
 
 tag, launches_csv, rep = sys.argv[1:4]
+command = sys.argv[4] if len(sys.argv) > 4 else "python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-strong --no-ppo-line"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
@@ -24,7 +25,7 @@ for r in rows:
     d[1] += float(r[-1]) / 1e3
 total_us = sum(v[1] for v in tot.values())
 lines = [f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` over "
-         "`python bench.py --steps 30 --warmup 3 --no-cpu-baseline --e2e-steps 3 --no-rollout`", "",
+         f"`{command}`", "",
          "Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.", "",
          "| kernel | launches | total us | share | avg us |", "|---|---:|---:|---:|---:|"]
 for name, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
