@@ -231,7 +231,7 @@ typedef struct PtgStateSoA {
 int ptg_get_state(PtgHandle* h, const PtgStateSoA* out);
 int ptg_set_state(PtgHandle* h, const PtgStateSoA* in);
 
-/* Deterministic two-stage reduction (warp shuffles -> per-block partials -> one block) of the finished-episode
+/* Deterministic reduction in one launch (warp shuffles -> per-block partials -> the last block folds them in index order) of the finished-episode
  * accumulators into *stats_dev (device, 64 bytes); clear != 0 zeroes the accumulators afterwards. */
 int ptg_episode_stats(PtgHandle* h, PtgEpisodeStats* stats_dev, int clear, void* stream);
 

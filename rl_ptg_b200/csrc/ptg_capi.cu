@@ -46,6 +46,7 @@ struct PtgHandle {
     StatAcc* d_partial = nullptr;
     Sums* d_vn_partial = nullptr;     // per-CTA partial sums of the VecNormalize returns
     unsigned int* d_vn_ticket = nullptr;
+    unsigned int* d_stats_ticket = nullptr;
     uint32_t* d_err = nullptr;
     int32_t* d_state_i32 = nullptr;   // scratch for get/set state: 13 int32 arrays + state_changes
     int64_t* d_state_i64 = nullptr;
@@ -445,6 +446,8 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     PTG_TRY(h->alloc(&h->d_vn_partial, PTG_STATS_BLOCKS));
     PTG_TRY(h->alloc(&h->d_vn_ticket, 1));
     PTG_TRY(cudaMemset(h->d_vn_ticket, 0, sizeof(unsigned int)));
+    PTG_TRY(h->alloc(&h->d_stats_ticket, 1));
+    PTG_TRY(cudaMemset(h->d_stats_ticket, 0, sizeof(unsigned int)));
     PTG_TRY(h->alloc(&h->d_state_i32, n * 14)); PTG_TRY(h->alloc(&h->d_state_i64, n)); PTG_TRY(h->alloc(&h->d_state_f64, n * 2));
     PTG_TRY(h->alloc(&h->d_state_rng, n * 4));
     P.tape = nullptr; P.tape_len = 0;
@@ -622,9 +625,10 @@ extern "C" int ptg_episode_stats(PtgHandle* h, PtgEpisodeStats* stats_dev, int c
     int rc = check_device(h, "ptg_episode_stats");
     if (rc != PTG_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    k_stats_partial<<<PTG_STATS_BLOCKS, 256, 0, st>>>(h->P, h->d_partial, clear);
-    k_stats_final<<<1, 256, 0, st>>>(h->d_partial, PTG_STATS_BLOCKS, h->total_steps, stats_dev);
-    h->launches += 2;
+    // one launch; small shards get one CTA per 1024 envs instead of the full 4 x 148
+    const unsigned grid = (unsigned)std::min<int64_t>(PTG_STATS_BLOCKS, std::max<int64_t>(1, (h->P.n_envs + 1023) / 1024));
+    k_episode_stats<<<grid, 256, 0, st>>>(h->P, h->d_partial, h->d_stats_ticket, clear, h->total_steps, stats_dev);
+    h->launches += 1;
     if (clear) h->total_steps = 0.0;
     PTG_CUDA(cudaGetLastError());
     return PTG_OK;

@@ -4,7 +4,7 @@
 //   k_construct    PTGEnv.__init__ for all envs
 //   k_reset        VecEnv.reset() / PTGEnv.reset(seed)
 //   k_step         VecEnv.step_wait(): T >= 1 env steps per launch, state in registers, SB3 auto-reset
-//   k_stats_*      deterministic two-stage reduction of finished-episode statistics (warp shuffles)
+//   k_episode_stats  deterministic reduction of finished-episode statistics (warp shuffles, last-CTA fold)
 //
 // The step kernel is HBM-bound streaming of per-env state + observation rows; the only gathers go to
 // L2-resident tables (step table 64 B/entry, hour row 16*NV B, day row 32 B, argmin LUT 4 B) and -- on a noise
@@ -1016,7 +1016,7 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// episode statistics: deterministic two-stage reduction
+// episode statistics: deterministic reduction in one launch
 // ------------------------------------------------------------------------------------------------------------
 struct StatAcc { double cnt, sum, sq, len, mn, mx; };
 
@@ -1046,7 +1046,10 @@ __device__ __forceinline__ StatAcc stat_block_reduce(StatAcc a) {
 
 #define PTG_STATS_BLOCKS 592   // 4 x 148 SMs
 
-__global__ void k_stats_partial(const __grid_constant__ DevParams P, StatAcc* partial, int clear) {
+// One launch: every CTA reduces its blocked env range to a partial; the LAST CTA to finish (atomic ticket) folds the
+// partials in index order -- the same fixed summation order whichever CTA that is -- and writes the record.
+__global__ void k_episode_stats(const __grid_constant__ DevParams P, StatAcc* partial, unsigned int* ticket, int clear,
+                                double total_steps, PtgEpisodeStats* out) {
     StatAcc a{0, 0, 0, 0, INFINITY, -INFINITY};
     // fixed env -> thread assignment (blocked ranges) so that the summation order never depends on timing
     const int64_t per_block = (P.n_envs + gridDim.x - 1) / gridDim.x;
@@ -1063,16 +1066,25 @@ __global__ void k_stats_partial(const __grid_constant__ DevParams P, StatAcc* pa
         }
     }
     a = stat_block_reduce(a);
-    if (threadIdx.x == 0) partial[blockIdx.x] = a;
-}
-
-__global__ void k_stats_final(const StatAcc* partial, int n_partial, double total_steps, PtgEpisodeStats* out) {
-    StatAcc a{0, 0, 0, 0, INFINITY, -INFINITY};
-    for (int q = threadIdx.x; q < n_partial; q += blockDim.x) a = stat_combine(a, partial[q]);
-    a = stat_block_reduce(a);
+    __shared__ bool is_last;
     if (threadIdx.x == 0) {
-        out->count = a.cnt; out->sum_return = a.sum; out->sum_return_sq = a.sq; out->sum_length = a.len;
-        out->min_return = a.mn; out->max_return = a.mx; out->total_steps = total_steps; out->_reserved = 0.0;
+        partial[blockIdx.x] = a;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    StatAcc t{0, 0, 0, 0, INFINITY, -INFINITY};
+    for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {      // (L2 reads: the partials come from other SMs)
+        const double* pq = reinterpret_cast<const double*>(partial + q);
+        t = stat_combine(t, StatAcc{__ldcg(pq), __ldcg(pq + 1), __ldcg(pq + 2), __ldcg(pq + 3), __ldcg(pq + 4), __ldcg(pq + 5)});
+    }
+    t = stat_block_reduce(t);
+    if (threadIdx.x == 0) {
+        out->count = t.cnt; out->sum_return = t.sum; out->sum_return_sq = t.sq; out->sum_length = t.len;
+        out->min_return = t.mn; out->max_return = t.mx; out->total_steps = total_steps; out->_reserved = 0.0;
+        *ticket = 0u;
     }
 }
 
