@@ -569,7 +569,10 @@ def run_gpu(args):
                        "host_threads_per_rank": host_threads,
                        "episodes_finished": stats["episodes"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_step<4,true,false,false,13>",
+                         "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full "
+                         "(cold-cache replay; profiles/traffic_r*.json); below the algorithmic bytes because plant state and "
+                         "RNG records are served from / absorbed by the L2 (DESIGN.md section 3)",
+                         "peak_source": peak_src, "kernel": "k_step<4,true,false,false,13>",
                          "kernel_ms": kernel_ms},
             "cpu_baseline": cpu,
             "cpu_baseline_port": cpu_port,
