@@ -408,7 +408,16 @@ def run_gpu(args):
     barrier()
     launches = env.kernel_launches() - l0
     ms = ev0.elapsed_time(ev1)
-    draws_per_step = (total_draws() - draws0) / ((P + LEAD + K) * n_local)
+    # the same K steps once more with the first event directly behind the synchronisation (no lead steps): reported
+    # beside the headline as config.ms_per_step_without_lead_steps
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for t in range(K):
+        env.step_tensor(pool[(P + LEAD + K + t) % n_pool])
+    s1.record()
+    barrier()
+    ms_strict = s0.elapsed_time(s1)
+    draws_per_step = (total_draws() - draws0) / ((P + LEAD + 2 * K) * n_local)
     # secondary action distributions: the load-biased mix, and an agent-like "sticky" policy (each
     # env repeats one action, so almost no transition noise is drawn after warm-up)
     Ks = max(200, K)
@@ -543,6 +552,7 @@ def run_gpu(args):
                        "obs_dim": obs_dim, "noise": "on-device PCG64+ziggurat (numpy-exact)",
                        "preroll_steps": preroll_done, "untimed_single_steps_before_timed_region": P,
                        "untimed_steps_queued_ahead_of_the_first_event": LEAD,
+                       "ms_per_step_without_lead_steps": ms_strict / K,
                        "copy_gbs_this_box": copy_gbs,
                        "bytes_per_env_step": round(bpe, 2),
                        "bytes_per_env_step_breakdown": {"state_action_obs_reward_done": bpe0,
