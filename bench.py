@@ -453,6 +453,17 @@ def run_gpu(args):
         copy_gbs = 2 * ca.numel() * 4 / (best * 1e-3) / 1e9
         del ca, cb
 
+    box_probe = None
+    if rank == 0:
+        import ctypes
+        from rl_ptg_b200 import _lib
+        out4 = (ctypes.c_double * 4)()
+        _lib.check(_lib.load().ptg_probe_box(local_rank, ctypes.byref(out4)))
+        box_probe = {"l2_dependent_load_ns": round(out4[0], 1), "dram_dependent_load_ns": round(out4[1], 1),
+                     "sm_clock_mhz_seen_by_a_thread": round(out4[2], 1),
+                     "note": "the step kernel is bound by latency x occupancy, not by HBM bandwidth: boxes of this pool "
+                             "with the same copy bandwidth run the same binary 58 or 66 us per step (DESIGN.md section 7)"}
+
     # ---------------- rollout kernel (T steps per launch), reported in config ----------------
     T = 16
     acts_T = pool[:min(T, n_pool)].repeat((T + n_pool - 1) // n_pool, 1)[:T].contiguous()
@@ -553,7 +564,7 @@ def run_gpu(args):
                        "preroll_steps": preroll_done, "untimed_single_steps_before_timed_region": P,
                        "untimed_steps_queued_ahead_of_the_first_event": LEAD,
                        "ms_per_step_without_lead_steps": ms_strict / K,
-                       "copy_gbs_this_box": copy_gbs,
+                       "copy_gbs_this_box": copy_gbs, "box_probe": box_probe,
                        "bytes_per_env_step": round(bpe, 2),
                        "bytes_per_env_step_breakdown": {"state_action_obs_reward_done": bpe0,
                                                         "rng_state_per_draw": RNG_BYTES_PER_DRAW,

@@ -321,6 +321,10 @@ uint32_t ptg_last_step_serial(const PtgHandle* h);                       /* seri
 int ptg_host_standard_normal(uint64_t seed, int64_t n, double* out);
 /* PCG64 state after seeding: out[0..3] = state_hi, state_lo, inc_hi, inc_lo. */
 int ptg_host_seed_state(uint64_t seed, uint64_t* out4);
+/* Diagnostic, no reference counterpart: dependent-load latency of this GPU's L2 (out4[0], ns per hop over a 16 MB
+ * ring) and DRAM (out4[1], 256 MB ring) and the SM clock a lone thread is given (out4[2], MHz).  The step kernel is bound
+ * by latency x occupancy, so bench.py reports these beside its numbers (config.box_probe). */
+int ptg_probe_box(int device, double* out4);
 const char* ptg_last_error(void);
 int ptg_abi_version(void);
 

@@ -905,5 +905,55 @@ extern "C" int ptg_host_seed_state(uint64_t seed, uint64_t* out4) {
     return PTG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// box probe: dependent-load latency of the L2 and of DRAM and the SM clock actually delivered -- the step kernel is
+// bound by latency x occupancy, and the same binary differs by ~14 % between boxes of one pool with equal copy bandwidth
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_probe_chase(const uint32_t* next, int hops, uint32_t start, double* out_ns_per_hop, double* out_mhz) {
+    uint32_t p = start;
+    for (int q = 0; q < 2048; ++q) p = __ldcg(next + p);                   // warm the TLB / first touches
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    for (int q = 0; q < hops; ++q) p = __ldcg(next + p);                   // L1-bypassing dependent loads
+    const long long c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    *out_ns_per_hop = (double)(t1 - t0) / hops + (p == 0xffffffffu ? 1.0 : 0.0);
+    *out_mhz = (double)(c1 - c0) / (double)(t1 - t0) * 1e3;
+}
+}  // namespace
+
+extern "C" int ptg_probe_box(int device, double* out4) {
+    if (!out4) return fail(PTG_ERR_INVALID_ARGUMENT, "null output");
+    PTG_CUDA(cudaSetDevice(device));
+    double* d_out = nullptr;
+    PTG_CUDA(cudaMalloc(&d_out, 2 * sizeof(double)));
+    for (int pass = 0; pass < 2; ++pass) {                                  // 0: 16 MB ring (L2-resident), 1: 256 MB ring (DRAM)
+        const size_t n = pass == 0 ? (size_t)4 << 20 : (size_t)64 << 20;
+        std::vector<uint32_t> next(n);
+        // one cycle through all slots with a large odd stride (every hop lands in another line and DRAM page)
+        const uint64_t stride = 2654435761ull % n | 1ull;
+        for (size_t q = 0; q < n; ++q) next[q] = (uint32_t)((q + stride) % n);
+        uint32_t* d_next = nullptr;
+        PTG_CUDA(cudaMalloc(&d_next, n * sizeof(uint32_t)));
+        PTG_CUDA(cudaMemcpy(d_next, next.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (pass == 0) {                                                     // pull the ring into L2 once
+            k_probe_chase<<<1, 1>>>(d_next, (int)n, 0u, d_out, d_out + 1);
+            PTG_CUDA(cudaDeviceSynchronize());
+        }
+        k_probe_chase<<<1, 1>>>(d_next, 200000, 12345u, d_out, d_out + 1);
+        PTG_CUDA(cudaDeviceSynchronize());
+        double r[2];
+        PTG_CUDA(cudaMemcpy(r, d_out, sizeof(r), cudaMemcpyDeviceToHost));
+        out4[pass] = r[0];
+        out4[2] = r[1];
+        cudaFree(d_next);
+    }
+    out4[3] = 0.0;
+    cudaFree(d_out);
+    return PTG_OK;
+}
+
 extern "C" const char* ptg_last_error(void) { return g_last_error.c_str(); }
 extern "C" int ptg_abi_version(void) { return PTG_ABI_VERSION; }
