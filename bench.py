@@ -483,6 +483,31 @@ def run_gpu(args):
         roll_ms = e0.elapsed_time(e1) / (reps * T)
         del out
 
+    # ---------------- the flat observation layout (what a GPU policy consumes), reported in config ----------------
+    flat = None
+    if args.flat_line:
+        fenv = PtGVecEnv(kw, hi - lo, seed=3654, device=dev, env_id_offset=lo, n_envs_global=n_global, obs_layout="flat")
+        fenv.reset_tensor()
+        fout = fenv.rollout_tensor(acts_pre)
+        for _ in range(max(0, args.preroll_steps // T_pre - 1)):
+            fenv.rollout_tensor(acts_pre, out=fout)
+        del fout
+        fres = {}
+        for name, pl in (("uniform", pool), ("sticky", pool[:1].repeat(n_pool, 1).contiguous())):
+            for t in range(400):
+                fenv.step_tensor(pl[t % n_pool])
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for t in range(max(200, K)):
+                fenv.step_tensor(pl[t % n_pool])
+            f1.record()
+            torch.cuda.synchronize()
+            fres[name] = f0.elapsed_time(f1) / max(200, K)
+        flat = {"bytes_per_env_step_without_rng": fenv.bytes_per_env_step, "feature_dim": fenv.feature_dim,
+                "ms_per_step_uniform": fres["uniform"], "ms_per_step_sticky": fres["sticky"]}
+        fenv.close()
+        del fenv
+
     # ---------------- end to end through the numpy API ----------------
     acts_h = [pool[q].cpu().numpy() for q in range(n_pool)]
     Ke = max(3, min(K, args.e2e_steps))
@@ -585,6 +610,13 @@ def run_gpu(args):
                            "T": T, "ms_per_step": roll_ms,
                            "bytes_per_env_step": round(bpe - 64 + 64 / T, 2),     # state stays in registers between steps
                            "roofline_frac": (bpe - 64 + 64 / T) * n_local / (roll_ms * 1e-3) / 1e9 / peak},
+                       "flat_layout": None if flat is None else dict(
+                           flat, note="obs_layout='flat': the step kernel writes the [n_envs, 40] MultiInputPolicy feature rows "
+                                      "(one bulk store per warp) instead of the key-major Dict blocks",
+                           roofline_frac_uniform=(flat["bytes_per_env_step_without_rng"] + RNG_BYTES_PER_DRAW * draws_per_step)
+                           * n_local / (flat["ms_per_step_uniform"] * 1e-3) / 1e9 / peak,
+                           roofline_frac_sticky=flat["bytes_per_env_step_without_rng"] * n_local
+                           / (flat["ms_per_step_sticky"] * 1e-3) / 1e9 / peak),
                        "strong_scaling": strong,
                        "ppo": ppo,
                        "host_threads_per_rank": host_threads,
@@ -787,6 +819,8 @@ def main():
     ap.add_argument("--presteps", type=int, default=1024, help="untimed single steps right before the timed region (>= 10 ms)")
     ap.add_argument("--strong", action="store_true", default=True, help="BASELINE config 4 leg: 1M envs in total")
     ap.add_argument("--no-strong", dest="strong", action="store_false")
+    ap.add_argument("--no-flat-line", dest="flat_line", action="store_false", default=True,
+                    help="skip config.flat_layout (the same step with the flat feature-row observation layout)")
     ap.add_argument("--no-ppo-line", dest="ppo_line", action="store_false", default=True,
                     help="skip config.ppo (BASELINE config 5 as one small time-boxed line)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

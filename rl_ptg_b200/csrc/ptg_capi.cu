@@ -106,7 +106,7 @@ cudaError_t launch_pdl(K kernel, unsigned grid, cudaStream_t st, const DevParams
 template <int NV, bool MOD>
 cudaError_t launch_step_t(PtgHandle* h, const void* actions, int adtype, const PtgIO& io, int T, cudaStream_t st) {
     unsigned grid = blocks_for(h->P.n_envs, PTG_BLOCK);
-    if (h->P.flat && T == 0)   // single steps of the flat layout: persistent CTAs, one scheduling wave of them (see k_step)
+    if ((h->P.flat || PTG_PERSIST_ALL) && T == 0)   // persistent CTAs, one scheduling wave of them (see k_step)
         grid = std::min<unsigned>(grid, (unsigned)std::max(1, h->P.prefetch_distance / PTG_BLOCK));
     h->P.action_bytes = adtype == PTG_ACT_I64 ? 8 : adtype == PTG_ACT_U8 ? 1 : 4;
     const bool pa13 = NV == 4 && h->P.pa == 13;       // compile-time price_ahead for the reference default

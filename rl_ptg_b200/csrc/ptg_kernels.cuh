@@ -642,6 +642,15 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
 #ifndef PTG_PDL
 #define PTG_PDL 1
 #endif
+#ifndef PTG_TMA_AT_END
+#define PTG_TMA_AT_END 0         // 1: the staged window tiles go to the TMA at the end of the step instead of before the transition
+#endif
+#ifndef PTG_PERSIST_ALL
+#define PTG_PERSIST_ALL 1        // single steps run persistent CTAs in both layouts (0: key-major with one tile per CTA, round 1)
+#endif
+#ifndef PTG_LATE_WINDOWS
+#define PTG_LATE_WINDOWS 0       // 1: market-row gathers issued with the step-table gather instead of before the transition
+#endif
 #ifndef PTG_STEP_MIN_BLOCKS
 #define PTG_STEP_MIN_BLOCKS 4        // CTAs of 256 threads per SM the step kernel is compiled for (<= 64 registers)
 #endif
@@ -754,21 +763,35 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         // the market-window blocks of the observation only move when the clock crosses an hour (or the episode ends)
         win_moved = done || (sec / 3600u) != ((sec - (unsigned)P.sim_step) / 3600u);
         clamp_market_index(P, t_hour, t_day);
-        load_hour_row<NV>(P, t_hour, hrow);
-        day = load_day_row(P, t_day);
         int k1 = k + 1;
         PTG_CHECK_INDEX(P, k1, P.eps_sim_steps + 1, 5);
+#if !PTG_LATE_WINDOWS
+        load_hour_row<NV>(P, t_hour, hrow);
+        day = load_day_row(P, t_day);
         const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
         stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
         const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
-        // the window tiles go to the TMA before the transition: the fence in front of a bulk store waits for the
-        // thread's outstanding accesses, so it must not sit behind the RNG / step-table requests
+#if !PTG_TMA_AT_END
         if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
+#endif
+#endif
         // (3) plant transition (requests the RNG record when it draws) -> step-table entry (2 x 32 B sectors)
         const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep);
         const int state_change = (prev_state != (int)(meta & 7));
         U256 qc, qn;      // qc = {c_gas, c_eua, c_el, c_0}, qn = {norm[6], tinfo, pad}
         gather_step_entry(P, ent, lane, nvalid, qc, qn);
+#if PTG_LATE_WINDOWS
+        // The market rows are requested TOGETHER with the step-table entry: the two gathers were the two longest
+        // waits of a step (14 % and 17 % of the stall samples) and depended on nothing but each other's position in
+        // the code.  The hour row is not live across the transition (no spills), and the window staging below runs
+        // while the step-table entry is still in flight.
+        load_hour_row<NV>(P, t_hour, hrow);
+        day = load_day_row(P, t_day);
+        const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
+        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
+        const double el = hour_row_el<NV>(hrow);
+        if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
+#endif
         // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
         const double c_gas = __longlong_as_double((long long)qc.a), c_eua = __longlong_as_double((long long)qc.b);
         const double c_el = __longlong_as_double((long long)qc.c), c_0 = __longlong_as_double((long long)qc.d);
@@ -809,7 +832,9 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         day = DayRow{};
         o = ObsRegs{};
         stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
+#if !PTG_TMA_AT_END
         if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
+#endif
     }
     // episode ends are rare: only then is the warp's window tile staged again, from re-read hour rows (the reset
     // observation of the done lanes, the unchanged rows of the others), and stored after the fact
@@ -826,6 +851,9 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         st_stream(rew_out + e, reward);
         st_stream(done_out + e, (uint8_t)done);
     }
+#if PTG_TMA_AT_END && !PTG_LATE_WINDOWS
+    if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
+#endif
     if (single && io.windows_changed != nullptr && __any_sync(0xffffffffu, win_moved) && lane == 0)
         *io.windows_changed = P.step_serial;        // (same value from every warp: plain store, no atomic needed)
 }
@@ -951,11 +979,13 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     // ... and nothing the previous kernel may still be writing (env state, actions) is touched before it completed
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
-    // The flat layout runs PERSISTENT CTAs (tile b, b + gridDim, ...; the L2 prefetch below then targets the CTA's
-    // own next tile): its single end-of-step bulk store would otherwise hold the CTA's slot for ~10 % of its lifetime
-    // while the TMA reads the tile; with a next tile to work on, that wait disappears (63.7 -> 58.1 us).  The
-    // key-major layout hands its tiles to the TMA early and is faster with one tile per CTA (54 vs 56.5 us).
-    constexpr bool PERSIST = FLAT && !MANY;             // (the roll-out kernel's stores overlap its next step anyway)
+    // Single steps run PERSISTENT CTAs (one scheduling wave of them, tile b, b + gridDim, ...): a warp that finishes a
+    // tile starts its next one without waiting for the seven other warps of its CTA to drain and for a new CTA to be
+    // scheduled, and the ziggurat table is staged once per CTA instead of once per tile.  Flat layout: 63.7 -> 58.1 us
+    // (round 1: its end-of-step bulk store otherwise holds the CTA's slot while the TMA reads the tile).  Key-major
+    // layout: round 1 measured the opposite (56.5 vs 54 us, with the L2 state prefetch); with the plant state resident
+    // in L2 and the prefetch gone it is 56.5 vs 58.3 us uniform, 41.8 vs 42.7 us sticky (round 2, same box).
+    constexpr bool PERSIST = (FLAT || PTG_PERSIST_ALL) && !MANY;   // (the roll-out kernel's stores overlap its next step anyway)
     if (PERSIST && use_zig) __syncthreads();            // ziggurat table visible to every warp of the CTA
     for (int tile = blockIdx.x; tile * PTG_BLOCK < n_envs; tile += gridDim.x) {
     const int e = tile * PTG_BLOCK + (int)threadIdx.x;
