@@ -396,6 +396,15 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
         PTG_TRY(h->upload(&P.chain_tab, chain.data(), chain.size()));
         P.chain_top = top;
     }
+    {   // the (action, state, T flags, hot_cold) part of the 5x5 dispatch, evaluated literally for every combination
+        std::vector<uint16_t> lut(PTG_PLAN_LUT_SIZE, 0);
+        for (int a = 0; a < 5; ++a)
+            for (int st = 0; st < 5; ++st)
+                for (int tf = 0; tf < 8; ++tf)
+                    for (uint32_t hot = 0; hot < 2; ++hot)
+                        lut[(size_t)plan_lut_index(a, st, tf, hot)] = (uint16_t)plan_pack(a, st, tf, hot);
+        PTG_TRY(h->upload(&P.plan_lut, lut.data(), lut.size()));
+    }
     if (tables->eps_ind) PTG_TRY(h->upload(&P.eps_ind, tables->eps_ind, (size_t)tables->n_eps_ind));
     else P.eps_ind = nullptr;
 

@@ -245,6 +245,7 @@ struct DevParams {
     const DayRow* day_tab;         // [n_days]
     const ClockRow* clock_tab;     // [eps_sim_steps + 1]
     const int64_t* eps_ind;        // [n_eps_ind] or nullptr
+    const uint16_t* plan_lut;      // [PTG_PLAN_LUT_SIZE] plan_pack() of every (action, state, T flags, hot_cold)
     const uint32_t* chain_tab;     // [4][chain_top + 1] chain_pack() entries
     int32_t chain_top;             // time_op values >= chain_top share the last entry
     const double* pot0;            // e_r_b[1, 0, :] fp64 (info "Pot_Reward")
@@ -441,35 +442,49 @@ struct Plan {
     int kind, ds, col;       // col = argmin-LUT column or -1
 };
 
-__device__ __forceinline__ Plan plan_transition(int action, uint32_t& meta, int tflags) {
-    // hot/cold hysteresis (:339-342) and current_action (:347) are updated first, like the reference does
-    uint32_t hot = (tflags & PTG_TF_COLD) ? 0u : (tflags & PTG_TF_HOT) ? 1u : ((meta >> 3) & 1u);
-    meta = (meta & ~(0xfu << 3)) | (hot << 3) | ((uint32_t)action << 4);
-    const int state = meta & 7;
+// The part of the plan that only depends on (action, Meth_State, T flags, hot_cold): evaluated once per combination on
+// the host (ptg_create -> DevParams.plan_lut, 400 x uint16) so that the step kernel replaces three divergent branches
+// by one shared-memory look-up.  Packed: [0,2) kind | [2,7) table of a DRAW transition | [7,10) argmin-LUT column + 1
+// (0 = none) | bit 10 hot_cold after the hysteresis (:339-342).
+PTG_HD uint32_t plan_pack(int action, int state, int tflags, uint32_t hot_old) {
+    const uint32_t hot = (tflags & PTG_TF_COLD) ? 0u : (tflags & PTG_TF_HOT) ? 1u : hot_old;
     // the 5x5 match (:368-440): bit (5*action + state) set <=> the step continues the current table
     const uint32_t CONT = (1u << 0) | (1u << 6) | (7u << 12) | (15u << 15) | (7u << 20) | (1u << 24);
-    Plan p;
-    p.col = -1;
+    uint32_t kind, ds = 0, col1 = 0;
     if ((CONT >> (5 * action + state)) & 1u) {
-        p.kind = PTG_KIND_CONT;
-        p.ds = meta_tab(meta, state);
+        kind = PTG_KIND_CONT;
     } else if (action <= PTG_STARTUP) {
-        p.kind = PTG_KIND_DRAW;
-        p.ds = action == PTG_STANDBY ? ((tflags & PTG_TF_SBUP) ? PTG_DS_STANDBY_UP : PTG_DS_STANDBY_DOWN)      // :579-582
-             : action == PTG_COOLDOWN ? PTG_DS_COOLDOWN
-                                      : (hot ? PTG_DS_STARTUP_HOT : PTG_DS_STARTUP_COLD);                     // :616-619
+        kind = PTG_KIND_DRAW;
+        ds = action == PTG_STANDBY ? ((tflags & PTG_TF_SBUP) ? PTG_DS_STANDBY_UP : PTG_DS_STANDBY_DOWN)        // :579-582
+           : action == PTG_COOLDOWN ? PTG_DS_COOLDOWN
+                                    : (hot ? PTG_DS_STARTUP_HOT : PTG_DS_STARTUP_COLD);                       // :616-619
         // LUT column of table id 0..5: startup_cold 3, startup_hot 4, cooldown 0, standby_down 2, standby_up 1, op1 5
-        p.col = (0x512043 >> (4 * p.ds)) & 15;
-    } else if (action == PTG_PARTIAL_LOAD) {
-        p.kind = PTG_KIND_PARTIAL;
-        p.ds = 0;
-        if (meta_tab(meta, PTG_FULL_LOAD) == PTG_DS_OP2_START_F) p.col = 5;      // may need argmin(op1_start_p), :641
+        col1 = ((0x512043u >> (4 * ds)) & 15u) + 1u;
     } else {
-        p.kind = PTG_KIND_FULL;
-        p.ds = 0;
+        kind = action == PTG_PARTIAL_LOAD ? PTG_KIND_PARTIAL : PTG_KIND_FULL;
     }
+    return kind | (ds << 2) | (col1 << 7) | (hot << 10);
+}
+#define PTG_PLAN_LUT_SIZE (25 * 16)
+PTG_HD int plan_lut_index(int action, int state, int tflags, uint32_t hot_old) {
+    return ((5 * action + state) << 4) | (tflags << 1) | (int)hot_old;
+}
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ Plan plan_transition(int action, uint32_t& meta, int tflags, const uint16_t* plan_lut) {
+    const int state = meta & 7;
+    const uint32_t ent = plan_lut[plan_lut_index(action, state, tflags, (meta >> 3) & 1u)];
+    // hot/cold hysteresis (:339-342) and current_action (:347) are updated first, like the reference does
+    meta = (meta & ~(0xfu << 3)) | (((ent >> 10) & 1u) << 3) | ((uint32_t)action << 4);
+    Plan p;
+    p.kind = ent & 3u;
+    p.ds = (ent >> 2) & 31u;
+    p.col = (int)((ent >> 7) & 7u) - 1;
+    if (p.kind == PTG_KIND_CONT) p.ds = meta_tab(meta, state);
+    else if (p.kind == PTG_KIND_PARTIAL && meta_tab(meta, PTG_FULL_LOAD) == PTG_DS_OP2_START_F) p.col = 5;   // :641
     return p;
 }
+#endif
 
 __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, const Plan& p, int& i, int& j,
                                                 uint32_t& meta, int lut_val, const uint64_t* zig_kiwi,

@@ -729,7 +729,8 @@ __device__ __forceinline__ void gather_step_entry(const DevParams& P, int ent, i
 template <int NV, bool MOD, bool EVAL, int PAC>
 __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, long long action_raw, int adtype,
                                          bool single, int e, bool active, int lane, int warp_env0,
-                                         int nvalid, float* sm, const uint64_t* zig_kiwi, float* __restrict__ obs_out,
+                                         int nvalid, float* sm, const uint64_t* zig_kiwi, const uint16_t* plan_lut,
+                                         float* __restrict__ obs_out,
                                          float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int& i, int& j,
                                          int& k, uint32_t& meta, int32_t& tinfo, int2& ep, double& ep_ret) {
     float4 hrow[NV];
@@ -746,7 +747,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         // (1) what the transition will need from memory
         const int action = decode_action_raw(P, action_raw, adtype, (meta >> 4) & 7);
         const int prev_state = meta & 7;
-        const Plan plan = plan_transition(action, meta, tinfo & 7);
+        const Plan plan = plan_transition(action, meta, tinfo & 7, plan_lut);
         uint32_t draws_ep = ti_draws(tinfo);
         int lut_val = 0;
         if (plan.col >= 0) {
@@ -864,7 +865,8 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
 template <bool MOD>
 __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& io, long long action_raw, int adtype,
                                               bool single, int e, bool active, int lane, int warp_env0, int nvalid,
-                                              float* sm, const uint64_t* zig_kiwi, float* __restrict__ obs_out,
+                                              float* sm, const uint64_t* zig_kiwi, const uint16_t* plan_lut,
+                                              float* __restrict__ obs_out,
                                               float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int& i,
                                               int& j, int& k, uint32_t& meta, int32_t& tinfo, int2& ep, double& ep_ret) {
     constexpr int F = PTG_FLAT_F(MOD);
@@ -879,7 +881,7 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
     if (active) {
         const int action = decode_action_raw(P, action_raw, adtype, (meta >> 4) & 7);
         const int prev_state = meta & 7;
-        const Plan plan = plan_transition(action, meta, tinfo & 7);
+        const Plan plan = plan_transition(action, meta, tinfo & 7, plan_lut);
         uint32_t draws_ep = ti_draws(tinfo);
         int lut_val = 0;
         if (plan.col >= 0) {
@@ -959,6 +961,7 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     static_assert(!FLAT || (NV == 4 && PAC == 13 && !EVAL), "the flat layout is built for price_ahead == 13");
     __shared__ __align__(128) float stage[PTG_BLOCK / 32][FLAT ? 32 * PTG_FLAT_F(MOD) : 2 * PTG_STAGE_FLOATS(NV)];
     __shared__ __align__(16) uint64_t zig_kiwi[2 * 256];   // {ki, wi} of numpy's ziggurat: 4 KB, one LDS.128 per draw
+    __shared__ __align__(4) uint16_t plan_lut[PTG_PLAN_LUT_SIZE];   // plan_pack() of every (action, state, T flags, hot_cold)
     static_assert(256 % PTG_BLOCK == 0, "the CTA stages the 256 ziggurat layers in 256 / PTG_BLOCK rounds");
     const int n_envs = (int)P.n_envs;                   // < 2^26 (checked by ptg_create): 32-bit index arithmetic
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -968,6 +971,8 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     // one has started, so its prologue (ziggurat table staging below) overlaps this kernel's tail wave ...
     asm volatile("griddepcontrol.launch_dependents;");
 #endif
+    for (int q = threadIdx.x; q < PTG_PLAN_LUT_SIZE / 2; q += PTG_BLOCK)
+        reinterpret_cast<uint32_t*>(plan_lut)[q] = __ldg(reinterpret_cast<const uint32_t*>(P.plan_lut) + q);
     if (use_zig) {
 #pragma unroll
         for (int q = threadIdx.x; q < 256; q += PTG_BLOCK) {
@@ -986,7 +991,7 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     // layout: round 1 measured the opposite (56.5 vs 54 us, with the L2 state prefetch); with the plant state resident
     // in L2 and the prefetch gone it is 56.5 vs 58.3 us uniform, 41.8 vs 42.7 us sticky (round 2, same box).
     constexpr bool PERSIST = (FLAT || PTG_PERSIST_ALL) && !MANY;   // (the roll-out kernel's stores overlap its next step anyway)
-    if (PERSIST && use_zig) __syncthreads();            // ziggurat table visible to every warp of the CTA
+    if (PERSIST) __syncthreads();                       // staged tables visible to every warp of the CTA
     for (int tile = blockIdx.x; tile * PTG_BLOCK < n_envs; tile += gridDim.x) {
     const int e = tile * PTG_BLOCK + (int)threadIdx.x;
     const int warp_env0 = e - lane;
@@ -1000,7 +1005,7 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     int2 ep = PTG_LD_STATE(P.ep + le);
     double ep_ret = PTG_LD_STATE(P.ep_ret + le);
     long long action_raw = load_action_raw(actions, adtype, le);
-    if (!PERSIST && use_zig) __syncthreads();           // (one tile per CTA: the barrier sits behind the state loads)
+    if (!PERSIST) __syncthreads();                      // (one tile per CTA: the barrier sits behind the state loads)
     if (!warp_in_range) continue;                       // whole warp out of range
     int i = core.x, j = core.y, k = core.z;
     uint32_t meta = (uint32_t)core.w;
@@ -1020,9 +1025,9 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
     const uint64_t* zig = use_zig ? zig_kiwi : nullptr;
     if (!MANY) {
         if (FLAT) step_one_flat<MOD>(P, io, action_raw, adtype, true, e, active, lane, warp_env0, nvalid, stage[wid], zig,
-                                     io.obs, io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
+                                     plan_lut, io.obs, io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
         else step_one<NV, MOD, EVAL, PAC>(P, io, action_raw, adtype, true, e, active, lane, warp_env0, nvalid, stage[wid],
-                                          zig, io.obs, io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
+                                          zig, plan_lut, io.obs, io.reward, io.done, i, j, k, meta, tinfo, ep, ep_ret);
     } else {
         for (int t = 0; t < T; ++t) {
             const long long a_now = action_raw;
@@ -1031,9 +1036,9 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
             float* rew_t = io.reward + (int64_t)t * n_envs;
             uint8_t* done_t = io.done + (int64_t)t * n_envs;
             if (FLAT) step_one_flat<MOD>(P, io, a_now, adtype, false, e, active, lane, warp_env0, nvalid, stage[wid], zig,
-                                         obs_t, rew_t, done_t, i, j, k, meta, tinfo, ep, ep_ret);
+                                         plan_lut, obs_t, rew_t, done_t, i, j, k, meta, tinfo, ep, ep_ret);
             else step_one<NV, MOD, false, PAC>(P, io, a_now, adtype, false, e, active, lane, warp_env0, nvalid, stage[wid],
-                                               zig, obs_t, rew_t, done_t, i, j, k, meta, tinfo, ep, ep_ret);
+                                               zig, plan_lut, obs_t, rew_t, done_t, i, j, k, meta, tinfo, ep, ep_ret);
         }
     }
     if (active) {
