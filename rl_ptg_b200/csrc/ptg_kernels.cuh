@@ -228,6 +228,14 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint3
                  ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 #endif
 }
+// One lane of the (converged) warp, chosen by the hardware: unlike `lane == 0`, `elect.sync` tells ptxas that exactly
+// one thread issues the bulk copies, so their operands move to uniform registers without a waterfall loop per copy
+// (43 instead of 77 SASS instructions between the proxy fence and the bulk-group flush).
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores of this thread have finished READING shared memory (the staging buffer may be rewritten)
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -240,9 +248,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // and warp -- 128*pa contiguous bytes -- issued by lane 0; the nine scalar keys are plain coalesced stores.
 // PAC > 0 fixes price_ahead at compile time (the reference default 13) so the staging stores need no predicates.
 template <int NV, bool MOD, int PAC>
-__device__ __forceinline__ void stage_windows(const DevParams& P, float* sm, int lane, const float4 (&hrow)[NV]) {
+__device__ __forceinline__ void stage_windows(const DevParams& P, float* sm, int lane, const float4 (&hrow)[NV],
+                                              bool full_warp) {
     const int pa = PAC > 0 ? PAC : P.pa;
-    if (lane == 0) tma_store_wait_read();         // previous step's bulk stores (rollout kernel) are done with sm
+    // previous bulk stores (roll-out kernel, persistent CTAs) are done with sm.  Bulk groups belong to the thread that
+    // issued them -- the elected lane; a ragged warp never issues any (and may get here from divergent code, where
+    // elect.sync must not run)
+    if (full_warp) { if (elect_one()) tma_store_wait_read(); }
     __syncwarp();
     float w[4 * NV];
 #pragma unroll
@@ -273,7 +285,7 @@ __device__ __forceinline__ void issue_window_stores(const DevParams& P, float* _
     if (nvalid == 32) {
         fence_proxy_async_smem();                 // make the generic-proxy writes visible to the async proxy
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
             tma_store_1d(gA, smA, 128u * (uint32_t)pa);
             if (MOD) tma_store_1d(gB, smB, 128u * (uint32_t)pa);
             tma_store_commit();
@@ -315,7 +327,7 @@ template <int NV, bool MOD>
 __device__ __forceinline__ void emit_obs(const DevParams& P, float* __restrict__ obs, float* sm, int e,
                                          bool active, int lane, int warp_env0, int nvalid,
                                          const float4 (&hrow)[NV], const DayRow& day, const ObsRegs& o) {
-    stage_windows<NV, MOD, 0>(P, sm, lane, hrow);
+    stage_windows<NV, MOD, 0>(P, sm, lane, hrow, nvalid == 32);
     flush_obs<NV, MOD, 0>(P, obs, sm, e, active, lane, warp_env0, nvalid, day, o);
 }
 
@@ -600,7 +612,7 @@ __global__ void __launch_bounds__(PTG_BLOCK) k_reset(const __grid_constant__ Dev
         else if (mask == nullptr) emit_obs<NV, MOD>(P, io.obs, stage[wid], e, active, lane, warp_env0, nvalid, hrow, day, o);
         else if (doit) emit_obs_scalar<NV, MOD>(P, io.obs, e, ObsKey{-1, t_hour, t_day, PTG_COOLDOWN, 0});
     }
-    if (lane == 0) tma_store_wait_read();
+    if (elect_one()) tma_store_wait_read();
     if (doit && io.info != nullptr) {
         write_info<NV>(P, io.info, e, InfoKey{0, t_hour, t_day, -1, 0, meta_pack(m), 0.0, 0.0});
     }
@@ -642,14 +654,8 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
 #ifndef PTG_PDL
 #define PTG_PDL 1
 #endif
-#ifndef PTG_TMA_AT_END
-#define PTG_TMA_AT_END 0         // 1: the staged window tiles go to the TMA at the end of the step instead of before the transition
-#endif
 #ifndef PTG_PERSIST_ALL
 #define PTG_PERSIST_ALL 1        // single steps run persistent CTAs in both layouts (0: key-major with one tile per CTA, round 1)
-#endif
-#ifndef PTG_LATE_WINDOWS
-#define PTG_LATE_WINDOWS 0       // 1: market-row gathers issued with the step-table gather instead of before the transition
 #endif
 #ifndef PTG_STEP_MIN_BLOCKS
 #define PTG_STEP_MIN_BLOCKS 4        // CTAs of 256 threads per SM the step kernel is compiled for (<= 64 registers)
@@ -766,33 +772,19 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         clamp_market_index(P, t_hour, t_day);
         int k1 = k + 1;
         PTG_CHECK_INDEX(P, k1, P.eps_sim_steps + 1, 5);
-#if !PTG_LATE_WINDOWS
         load_hour_row<NV>(P, t_hour, hrow);
         day = load_day_row(P, t_day);
         const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
-        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
+        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow, nvalid == 32);
         const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
-#if !PTG_TMA_AT_END
+        // the window tiles go to the TMA before the transition: the fence in front of a bulk store waits for the
+        // thread's outstanding accesses, so it must not sit behind the RNG / step-table requests
         if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
-#endif
-#endif
         // (3) plant transition (requests the RNG record when it draws) -> step-table entry (2 x 32 B sectors)
         const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep);
         const int state_change = (prev_state != (int)(meta & 7));
         U256 qc, qn;      // qc = {c_gas, c_eua, c_el, c_0}, qn = {norm[6], tinfo, pad}
         gather_step_entry(P, ent, lane, nvalid, qc, qn);
-#if PTG_LATE_WINDOWS
-        // The market rows are requested TOGETHER with the step-table entry: the two gathers were the two longest
-        // waits of a step (14 % and 17 % of the stall samples) and depended on nothing but each other's position in
-        // the code.  The hour row is not live across the transition (no spills), and the window staging below runs
-        // while the step-table entry is still in flight.
-        load_hour_row<NV>(P, t_hour, hrow);
-        day = load_day_row(P, t_day);
-        const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
-        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
-        const double el = hour_row_el<NV>(hrow);
-        if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
-#endif
         // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
         const double c_gas = __longlong_as_double((long long)qc.a), c_eua = __longlong_as_double((long long)qc.b);
         const double c_el = __longlong_as_double((long long)qc.c), c_0 = __longlong_as_double((long long)qc.d);
@@ -832,10 +824,8 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         for (int v = 0; v < NV; ++v) hrow[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         day = DayRow{};
         o = ObsRegs{};
-        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow);
-#if !PTG_TMA_AT_END
+        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow, nvalid == 32);
         if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
-#endif
     }
     // episode ends are rare: only then is the warp's window tile staged again, from re-read hour rows (the reset
     // observation of the done lanes, the unchanged rows of the others), and stored after the fact
@@ -844,7 +834,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
 #pragma unroll
         for (int v = 0; v < NV; ++v) h2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) load_hour_row<NV>(P, t_hour_out, h2);
-        stage_windows<NV, MOD, PAC>(P, sm, lane, h2);
+        stage_windows<NV, MOD, PAC>(P, sm, lane, h2, nvalid == 32);
         issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
     }
     if (active) {
@@ -852,9 +842,6 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         st_stream(rew_out + e, reward);
         st_stream(done_out + e, (uint8_t)done);
     }
-#if PTG_TMA_AT_END && !PTG_LATE_WINDOWS
-    if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
-#endif
     if (single && io.windows_changed != nullptr && __any_sync(0xffffffffu, win_moved) && lane == 0)
         *io.windows_changed = P.step_serial;        // (same value from every warp: plain store, no atomic needed)
 }
@@ -876,7 +863,7 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
     float reward = 0.f, pf0 = 0.f, pr12 = 0.f;
     const int done = active && (k == P.eps_sim_steps - 6);
     float* row = sm + lane * F;
-    if (lane == 0) tma_store_wait_read();         // the previous step's bulk store (rollout kernel) is done with the tile
+    if (elect_one()) tma_store_wait_read();       // the previous step's bulk store (rollout kernel) is done with the tile
     __syncwarp();
     if (active) {
         const int action = decode_action_raw(P, action_raw, adtype, (meta >> 4) & 7);
@@ -941,7 +928,7 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
     if ((bytes & 15u) == 0) {
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) { tma_store_1d(g, sm, bytes); tma_store_commit(); }
+        if (elect_one()) { tma_store_1d(g, sm, bytes); tma_store_commit(); }
     } else {                                          // ragged tail of the raw design: plain stores
         __syncwarp();
         for (int idx = lane; idx < nvalid * F; idx += 32) g[idx] = sm[idx];
@@ -1047,7 +1034,7 @@ k_step(const __grid_constant__ DevParams P, const void* __restrict__ actions, in
         PTG_ST_STATE(P.ep_ret + e, ep_ret);
     }
     }
-    if (lane == 0) tma_store_wait_read();               // the staging buffer must outlive the bulk stores' reads
+    if (elect_one()) tma_store_wait_read();             // the staging buffer must outlive the bulk stores' reads
 }
 
 // ------------------------------------------------------------------------------------------------------------
