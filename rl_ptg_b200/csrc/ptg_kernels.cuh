@@ -654,6 +654,9 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
 #ifndef PTG_PDL
 #define PTG_PDL 1
 #endif
+#ifndef PTG_PAIR_GATHER
+#define PTG_PAIR_GATHER 1        // step-table gather: lane pairs split their two entries (half the L1 wavefronts, +29 instructions)
+#endif
 #ifndef PTG_PERSIST_ALL
 #define PTG_PERSIST_ALL 1        // single steps run persistent CTAs in both layouts (0: key-major with one tile per CTA, round 1)
 #endif
@@ -709,7 +712,7 @@ __device__ __forceinline__ int decode_action_raw(const DevParams& P, long long r
 // warp a lane PAIR splits its two entries so that each LDG.256 touches 16 lines instead of 32 (even lane: first
 // halves, odd lane: second halves), then the halves are exchanged with four 64-bit shuffles.
 __device__ __forceinline__ void gather_step_entry(const DevParams& P, int ent, int lane, int nvalid, U256& qc, U256& qn) {
-    if (nvalid == 32) {
+    if (nvalid == 32 && PTG_PAIR_GATHER) {
         const int ent_p = __shfl_xor_sync(0xffffffffu, ent, 1);
         const bool odd = lane & 1;
         const char* base = reinterpret_cast<const char*>(P.step_tab) + (odd ? 32 : 0);
