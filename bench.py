@@ -631,9 +631,10 @@ def run_gpu(args):
             "cpu_baseline_port": cpu_port,
             "e2e": {"value": n_global * Ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "d2h_bytes_per_step_if_every_block_travelled": d2h_full,
-                    "steps": Ke, "note": "numpy VecEnv.step(): int64 action array in, converted to uint8 on the wire; "
-                                         "the market-window blocks (109 of 147 MB) are re-read only on steps that "
-                                         "move them (clock crosses an hour / episode end)"},
+                    "steps": Ke, "note": "numpy VecEnv.step(): int64 action array in, uint8 on the wire; METH_STATUS "
+                                         "comes back as one byte per env, the clock-encoding blocks not at all while all "
+                                         "envs share one clock, the market-window blocks (109 of 147 MB) only on steps "
+                                         "that move them (clock crosses an hour / episode end)"},
             "gpu_launches": launches,
             "clocks": clocks,
         }

@@ -154,6 +154,8 @@ typedef struct PtgIO {
                                   word and the caller does not have to: a host mirror that finds a value other than
                                   the serial of the step it just issued may skip the transfer of those blocks (3/4 of
                                   the observation bytes). */
+    uint8_t* status_u8;      /* [n_envs] or NULL (ptg_step): METH_STATUS of the returned observation as one byte per env
+                                -- what a host mirror transfers instead of the 4-byte block of the obs buffer */
 } PtgIO;
 
 /* One observation key of the obs buffer. */
@@ -315,6 +317,13 @@ int64_t ptg_obs_elems(const PtgHandle* h);                       /* fp32 element
 int64_t ptg_num_envs(const PtgHandle* h);
 int64_t ptg_bytes_per_env_step(const PtgHandle* h, int action_dtype);    /* algorithmic HBM bytes, DESIGN.md */
 int ptg_kernel_launches(const PtgHandle* h, int64_t* out);               /* kernels launched by this handle */
+/* Do all envs of the handle share one episode clock?  True from ptg_create / an unmasked ptg_reset on, as long as every
+ * env is stepped by the same calls (always the case) and no masked reset or ptg_set_state intervened -- tracked on the
+ * host, no device work.  Returns 1 and the clock encodings of the latest returned observation (Temp_hour_enc_sin / _cos,
+ * env/ptg_gym_env.py:449-450, the same fp32 values the kernels write) or 0.  A host mirror can then skip the transfer of
+ * those two blocks.  (Steps replayed from a captured CUDA graph do not pass through ptg_step and are not seen by this
+ * tracking: after a replay treat the clock as unknown until the next unmasked ptg_reset.) */
+int ptg_clock_uniform(const PtgHandle* h, float* sin_out, float* cos_out);
 uint32_t ptg_last_step_serial(const PtgHandle* h);                       /* serial of the latest ptg_step (see PtgIO.windows_changed) */
 /* Host twins of the on-device generator (no GPU needed): the first n values of
  * Generator(PCG64(SeedSequence(seed))).standard_normal() -- bit-identical to numpy; used by the CPU test-suite. */

@@ -85,7 +85,7 @@ class PtgOptLevel(C.Structure):
 class PtgIO(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("terminal_obs", C.c_void_p),
                 ("info", C.c_void_p), ("episode_return", C.c_void_p), ("episode_length", C.c_void_p),
-                ("windows_changed", C.c_void_p)]
+                ("windows_changed", C.c_void_p), ("status_u8", C.c_void_p)]
 
 
 class PtgObsKey(C.Structure):

@@ -18,7 +18,7 @@ EXPORTS = (
     "ptg_host_seed_state", "ptg_last_error",
     "ptg_abi_version", "ptg_vecnorm_moments", "ptg_vecnorm_apply", "ptg_features_dim", "ptg_features", "ptg_gae",
     "ptg_calculate_optimum", "ptg_allreduce_stats", "ptg_nccl_unique_id", "ptg_nccl_comm_create",
-    "ptg_nccl_comm_destroy", "ptg_last_step_serial", "ptg_probe_box",
+    "ptg_nccl_comm_destroy", "ptg_last_step_serial", "ptg_probe_box", "ptg_clock_uniform",
 )
 
 
@@ -65,6 +65,7 @@ def load(build_if_missing: bool = False):
     L.ptg_last_step_serial.argtypes = [vp]
     L.ptg_last_step_serial.restype = C.c_uint32
     L.ptg_probe_box.argtypes = [i32, C.POINTER(C.c_double * 4)]
+    L.ptg_clock_uniform.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     f64 = C.c_double
     L.ptg_vecnorm_moments.argtypes = [vp, vp, vp, f64, vp, vp, vp]
     L.ptg_vecnorm_apply.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, f64, f64, vp, vp]

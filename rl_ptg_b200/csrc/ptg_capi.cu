@@ -55,6 +55,8 @@ struct PtgHandle {
     PtgEpisodeStats* d_gather = nullptr;   // all-gather target of ptg_allreduce_stats
     int gather_ranks = 0;
     uint32_t step_serial = 0;
+    std::vector<float> clock_host;    // host copy of the clock table {sin, cos} per step index
+    int64_t uniform_k = 0;            // step counter shared by all envs, or -1 once they may differ
     int64_t launches = 0;
     double total_steps = 0.0;
 
@@ -421,6 +423,12 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     PTG_TRY(cudaDeviceSynchronize());
     PTG_TRY(cudaGetLastError());
 
+    {   // host copy of the clock encodings (ptg_clock_uniform)
+        std::vector<ClockRow> rows((size_t)c.eps_sim_steps + 1);
+        PTG_TRY(cudaMemcpy(rows.data(), clock_tab, rows.size() * sizeof(ClockRow), cudaMemcpyDeviceToHost));
+        h->clock_host.resize(rows.size() * 2);
+        for (size_t q = 0; q < rows.size(); ++q) { h->clock_host[2 * q] = rows[q].sin_h; h->clock_host[2 * q + 1] = rows[q].cos_h; }
+    }
     // ---- reset constants: i = argmin |cooldown.T - 16| (:118), flows = cooldown[i, 2:7] (:120-122) ----
     {
         const int v16 = (int)(std::lower_bound(tvals.begin(), tvals.end(), 16.0) - tvals.begin());
@@ -502,11 +510,21 @@ extern "C" int ptg_reset(PtgHandle* h, const int64_t* seeds, const uint8_t* mask
         PTG_CUDA(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, st));
         d_mask = h->d_mask;
     }
+    h->uniform_k = mask ? -1 : 0;
     cudaError_t lerr = cudaSuccess;
     PTG_DISPATCH(lerr, launch_reset_t, h, d_seeds, d_mask, *io, st);
     h->launches += 1;
     PTG_CUDA(lerr);
     return PTG_OK;
+}
+
+// the shared step counter after `steps` more steps: an episode ends when k reaches eps_sim_steps - 5 (:508-511) and,
+// with auto-reset, starts again at 0
+static void advance_clock(PtgHandle* h, int64_t steps) {
+    if (h->uniform_k < 0) return;
+    const int64_t ep_len = (int64_t)h->P.eps_sim_steps - 5;
+    if (h->P.auto_reset) h->uniform_k = (h->uniform_k + steps) % ep_len;
+    else h->uniform_k = h->uniform_k + steps <= (int64_t)h->P.eps_sim_steps ? h->uniform_k + steps : -1;
 }
 
 static int check_step_io(const PtgHandle* h, const void* actions, int adtype, const PtgIO* io) {
@@ -528,6 +546,7 @@ extern "C" int ptg_step(PtgHandle* h, const void* actions, int action_dtype, con
     PTG_DISPATCH(lerr, launch_step_t, h, actions, action_dtype, *io, 0, st);
     h->launches += 1;
     h->total_steps += (double)h->P.n_envs;
+    advance_clock(h, 1);
     PTG_CUDA(lerr);
     return PTG_OK;
 }
@@ -545,6 +564,7 @@ extern "C" int ptg_step_many(PtgHandle* h, const void* actions, int action_dtype
     PTG_DISPATCH(lerr, launch_step_t, h, actions, action_dtype, *io, (int)T, st);
     h->launches += 1;
     h->total_steps += (double)h->P.n_envs * T;
+    advance_clock(h, T);
     PTG_CUDA(lerr);
     return PTG_OK;
 }
@@ -619,6 +639,7 @@ extern "C" int ptg_set_state(PtgHandle* h, const PtgStateSoA* in) {
     PTG_CUDA(cudaMemcpy(s.cum_reward, in->cum_reward, n * sizeof(double), cudaMemcpyHostToDevice));
     PTG_CUDA(cudaMemcpy(s.rng, in->rng, n * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice));
     PTG_CUDA(cudaMemcpy(s.state_changes, in->state_changes, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    h->uniform_k = -1;
     k_state_pack<<<blocks_for(h->P.n_envs, 256), 256>>>(h->P, s, h->B);
     h->launches += 1;
     PTG_CUDA(cudaDeviceSynchronize());
@@ -891,6 +912,13 @@ extern "C" int64_t ptg_bytes_per_env_step(const PtgHandle* h, int action_dtype) 
 }
 
 extern "C" uint32_t ptg_last_step_serial(const PtgHandle* h) { return h ? h->step_serial : 0u; }
+
+extern "C" int ptg_clock_uniform(const PtgHandle* h, float* sin_out, float* cos_out) {
+    if (!h || h->uniform_k < 0 || (size_t)(2 * h->uniform_k + 1) >= h->clock_host.size()) return 0;
+    if (sin_out) *sin_out = h->clock_host[2 * (size_t)h->uniform_k];
+    if (cos_out) *cos_out = h->clock_host[2 * (size_t)h->uniform_k + 1];
+    return 1;
+}
 
 extern "C" int ptg_kernel_launches(const PtgHandle* h, int64_t* out) {
     if (!h || !out) return fail(PTG_ERR_INVALID_ARGUMENT, "null handle/out");

@@ -844,6 +844,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         store_obs_scalars<MOD>(P, obs_out, e, day, o);
         st_stream(rew_out + e, reward);
         st_stream(done_out + e, (uint8_t)done);
+        if (single && io.status_u8 != nullptr) st_stream(io.status_u8 + e, (uint8_t)o.status);
     }
     if (single && io.windows_changed != nullptr && __any_sync(0xffffffffu, win_moved) && lane == 0)
         *io.windows_changed = P.step_serial;        // (same value from every warp: plain store, no atomic needed)
@@ -939,6 +940,7 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
     if (active) {
         st_stream(rew_out + e, reward);
         st_stream(done_out + e, (uint8_t)done);
+        if (single && io.status_u8 != nullptr) st_stream(io.status_u8 + e, (uint8_t)o.status);
     }
 }
 

@@ -127,6 +127,7 @@ class StepGraph:
 
     def replay(self) -> None:
         self.env._win_valid = False
+        self.env._clock_ok = False          # (replayed steps do not pass through ptg_step's host-side clock tracking)
         self.graph.replay()
 
 
@@ -194,6 +195,9 @@ class PtGVecEnv(_Base):
         self._stats, self._stats_flip, self._stats_done, self._stats_ranks = self._stats_bufs[0], 0, [None, None], 1
         self.stats_stream = None                 # side stream of episode_stats_async(overlap=True), created on first use
         self._win_flag = torch.zeros(1, dtype=torch.int32, device=dev)     # PtgIO.windows_changed (step serial stamp)
+        self._status_d = torch.zeros(n, dtype=torch.uint8, device=dev)     # PtgIO.status_u8: METH_STATUS, one byte per env
+        self._status_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        self._clock_ok = True                    # the library's shared-clock tracking saw every step (no graph replays)
         self._obs_dict = self._obs_views(self._obs)          # views are created once; buffers are reused
         self._io = self._make_io(self._obs, self._reward, self._done, self._term_obs,
                                  self._info if self.cfg.train_or_eval else None, self._ep_ret, self._ep_len)
@@ -254,6 +258,7 @@ class PtGVecEnv(_Base):
         io.episode_return = ep_ret.data_ptr() if ep_ret is not None else None
         io.episode_length = ep_len.data_ptr() if ep_len is not None else None
         io.windows_changed = self._win_flag.data_ptr() if (reward is not None and self.obs_layout != "flat") else None
+        io.status_u8 = self._status_d.data_ptr() if reward is not None else None
         return io
 
     def _stream(self):
@@ -371,18 +376,23 @@ class PtGVecEnv(_Base):
         reward_h.copy_(self._reward, non_blocking=True)
         self._win_flag_h.copy_(self._win_flag, non_blocking=True)
         self._ev_small.record(stream)
-        # the scalar blocks (METH_STATUS first) travel ahead of the window blocks, so the int64 conversion of
-        # METH_STATUS overlaps the rest of the transfer
+        # METH_STATUS travels as one byte per env (PtgIO.status_u8) ahead of everything else, so its widening to int64
+        # overlaps the rest of the transfer; the 4-byte block of the obs buffer stays on the device
+        self._status_h.copy_(self._status_d, non_blocking=True)
+        self._ev_scalars.record(stream)
         cut = self._scalar_off
+        sin_v, cos_v = C.c_float(), C.c_float()
+        clock = None           # (sin, cos) shared by every env: those two blocks then need no transfer at all
+        if self._clock_ok and self._L.ptg_clock_uniform(self._h, C.byref(sin_v), C.byref(cos_v)):
+            clock = (np.float32(sin_v.value), np.float32(cos_v.value))
         if self.obs_layout == "flat":
             obs_h.copy_(self._obs, non_blocking=True)
-        else:                                       # METH_STATUS block, then the other eight scalar blocks
+            self.d2h_bytes += obs_h.numel() * 4 + self.num_envs * 6 + 4
+        else:                                       # the six plant scalar blocks (+ the clock blocks if envs differ)
             mid = cut + int(self._status_elems)
-            obs_h[cut:mid].copy_(self._obs[cut:mid], non_blocking=True)
-        self._ev_scalars.record(stream)
-        if self.obs_layout != "flat":
-            obs_h[mid:].copy_(self._obs[mid:], non_blocking=True)
-        self.d2h_bytes += (obs_h.numel() - cut) * 4 + self.num_envs * 5 + 4
+            end = mid + (6 if clock is not None else 8) * int(self._status_elems)
+            obs_h[mid:end].copy_(self._obs[mid:end], non_blocking=True)
+            self.d2h_bytes += (end - mid) * 4 + self.num_envs * 6 + 4
         eval_mode = bool(self.cfg.train_or_eval)
         if eval_mode:
             self._info_h.copy_(self._info, non_blocking=True)
@@ -399,8 +409,7 @@ class PtGVecEnv(_Base):
         rewards = reward_h.numpy()
         any_done = bool(dones.any())
         self._ev_scalars.synchronize()
-        status = self._obs_views(obs_h)["METH_STATUS"].numpy()
-        status = status.argmax(axis=1).astype(np.int64) if self.obs_layout == "flat" else status.astype(np.int64)
+        status = self._status_h.numpy().astype(np.int64)
         if any_done:
             self._term_obs_h.copy_(self._term_obs, non_blocking=True)
             self._ep_ret_h.copy_(self._ep_ret, non_blocking=True)
@@ -434,7 +443,12 @@ class PtGVecEnv(_Base):
             infos = LazyInfos(self.num_envs, None, make if (eval_mode or any_done) else None)
         else:
             infos = [make(e) for e in range(self.num_envs)]
-        return self._obs_numpy(obs_h, status=status, win_buf_h=self._obs_hh[self._win_buf]), rewards, dones, infos
+        obs = self._obs_numpy(obs_h, status=status, win_buf_h=self._obs_hh[self._win_buf])
+        if clock is not None and self.obs_layout != "flat":
+            # one value per block: handed out as read-only broadcast views (the kernels wrote the same fp32 values)
+            obs["Temp_hour_enc_sin"] = np.broadcast_to(clock[0].astype(self.obs_dtype), (self.num_envs, 1))
+            obs["Temp_hour_enc_cos"] = np.broadcast_to(clock[1].astype(self.obs_dtype), (self.num_envs, 1))
+        return obs, rewards, dones, infos
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None:
@@ -522,6 +536,8 @@ class PtGVecEnv(_Base):
             mask_p = mask.ctypes.data
         io = self._make_io(self._obs, None, None, None, self._info)
         _lib.check(self._L.ptg_reset(self._h, seeds_p, mask_p, C.byref(io), self._stream()))
+        if mask is None:
+            self._clock_ok = True
         self._win_valid = False
         self._reset_seeds()
         return self._obs_dict if _return_views else None

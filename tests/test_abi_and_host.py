@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_abi.PtgConfig) == 36 * 4 + 43 * 8
     assert _abi.PtgConfig.noise.offset == 144
     assert C.sizeof(_abi.PtgTables) == 17 * 8 * 2 + 6 * 8
-    assert C.sizeof(_abi.PtgIO) == 8 * 8
+    assert C.sizeof(_abi.PtgIO) == 9 * 8
     assert C.sizeof(_abi.PtgObsKey) == 40
     assert C.sizeof(_abi.PtgEpisodeStats) == 64
     assert C.sizeof(_abi.PtgStateSoA) == 18 * 8

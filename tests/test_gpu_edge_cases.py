@@ -307,7 +307,7 @@ def test_numpy_api_skips_unchanged_window_blocks_without_changing_results():
         a = rng.integers(0, 5, size=n)
         before = e1.d2h_bytes
         o1, r1, d1, _ = e1.step(a)
-        skipped += (e1.d2h_bytes - before) < e1.obs_elems * 4
+        skipped += (e1.d2h_bytes - before) < e1._scalar_off * 4      # less than the window blocks alone
         e2._win_valid = False                                  # force the full transfer
         o2, r2, d2, _ = e2.step(a)
         for k in o1:
@@ -545,4 +545,44 @@ def test_step_on_a_foreign_current_device_is_refused():
             env.step_tensor(a)
     assert ei.value.code == -1 and "current CUDA device" in str(ei.value)
     env.step_tensor(a)
+    env.close()
+
+
+def test_numpy_api_clock_blocks_with_and_without_a_shared_clock():
+    """The numpy API does not transfer Temp_hour_enc_sin / _cos while every env shares one episode clock (the library
+    tracks that on the host and hands out the two values) and METH_STATUS travels as one byte per env: both must equal
+    the device buffers exactly -- through an episode end, and after a masked reset has made the clocks differ (the
+    blocks travel again then)."""
+    kw = dict(synthetic_kwargs(dict(scenario=2, operation="OP2")))
+    kw["eps_sim_steps"] = 30                      # episodes of 25 steps
+    n = 700
+    env = make_env(kw, n, seed=21)
+    env.reset()
+    rng = np.random.default_rng(4)
+
+    def check(obs, what):
+        dev = {k: v.cpu().numpy() for k, v in env._obs_dict.items()}
+        for k in ("Temp_hour_enc_sin", "Temp_hour_enc_cos", "T_CAT", "Elec_Heating"):
+            assert np.array_equal(np.asarray(obs[k]).reshape(n), dev[k].reshape(n)), f"{k} {what}"
+        assert np.array_equal(obs["METH_STATUS"], dev["METH_STATUS"].reshape(n).astype(np.int64)), f"METH_STATUS {what}"
+
+    shared = 0
+    for t in range(60):                           # two episode ends
+        obs, _, done, _ = env.step(rng.integers(0, 5, size=n))
+        shared += int(obs["Temp_hour_enc_sin"].strides == (0, 0))
+        assert obs["Temp_hour_enc_sin"].shape == obs["T_CAT"].shape
+        check(obs, f"step {t}")
+    assert shared == 60                           # never transferred: broadcast views
+    mask = np.zeros(n, dtype=np.uint8)
+    mask[::3] = 1
+    env.reset_tensor(mask=mask)                   # a third of the envs restart: the clocks differ from here on
+    for t in range(30):
+        obs, _, done, _ = env.step(rng.integers(0, 5, size=n))
+        assert obs["Temp_hour_enc_sin"].strides != (0, 0)
+        check(obs, f"after the masked reset, step {t}")
+    assert len(np.unique(obs["Temp_hour_enc_cos"])) > 1
+    env.reset()                                   # an unmasked reset re-aligns them
+    obs, _, _, _ = env.step(rng.integers(0, 5, size=n))
+    assert obs["Temp_hour_enc_sin"].strides == (0, 0)
+    check(obs, "after the full reset")
     env.close()
