@@ -133,11 +133,13 @@ static_assert(sizeof(RngRec) == 32, "RngRec layout");
 #define PTG_L2_EVICT_FIRST 0x12F0000000000000ull
 #define PTG_L2_EVICT_LAST 0x14F0000000000000ull
 struct U256 { unsigned long long a, b, c, d; };
+// (256-bit accesses take the L2 eviction priority as an instruction modifier -- LDG.E.ELL2.256 -- instead of a policy
+//  operand: no pair of uniform-register moves in front of every gather)
 __device__ __forceinline__ U256 ldg256_nc(const void* p) {      // read-only tables (non-coherent path)
     U256 r;
 #if PTG_L2_HINTS
-    asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p), "l"(PTG_L2_EVICT_LAST));
+    asm volatile("ld.global.nc.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
 #else
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
 #endif
@@ -172,8 +174,8 @@ __device__ __forceinline__ U256 ld256(const void* p) {          // read-write da
 __device__ __forceinline__ U256 ld256_keep(const void* p) {
     U256 r;
 #if PTG_L2_HINTS
-    asm volatile("ld.global.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p), "l"(PTG_L2_EVICT_LAST) : "memory");
+    asm volatile("ld.global.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p) : "memory");
 #else
     r = ld256(p);
 #endif
