@@ -343,7 +343,7 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     PTG_TRY(h->upload(&d_erb, tables->e_r_b, (size_t)3 * P.pa * tables->n_hours));
     float* hour_tab = nullptr;
     PTG_TRY(h->alloc(&hour_tab, (size_t)tables->n_hours * P.nv * 4));
-    k_build_hour_tab<<<blocks_for(tables->n_hours, 128), 128>>>(d_erb, P.n_hours, P.pa, P.nv, P.raw,
+    k_build_hour_tab<<<blocks_for(tables->n_hours, 128), 128>>>(d_erb, P.n_hours, P.pa, P.nv, P.raw, P.flat,
                                                               P.raw ? c.el_l_b : c.rew_l_b, P.raw ? c.el_u_b : c.rew_u_b,
                                                               hour_tab, h->d_err);
     P.hour_tab = reinterpret_cast<const float4*>(hour_tab);

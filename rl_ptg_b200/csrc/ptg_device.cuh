@@ -488,9 +488,30 @@ __device__ __forceinline__ Plan plan_transition(int action, uint32_t& meta, int 
 }
 #endif
 
+// Load-change chain entry of a _partial / _full transition (:636-688, :702-754): only needs the state BEFORE the
+// transition, so the step kernel requests it together with the argmin-LUT value (PTG_CHAIN_EARLY) instead of inside
+// the divergent transition code, where the gather would only be issued after the noise-drawing lanes are done.
+#ifndef PTG_CHAIN_EARLY
+#define PTG_CHAIN_EARLY 1
+#endif
+__device__ __forceinline__ uint32_t chain_lookup(const DevParams& P, const Plan& p, uint32_t meta, int i, int j) {
+    const bool to_partial = p.kind == PTG_KIND_PARTIAL;
+    const uint32_t src = meta_tab(meta, to_partial ? PTG_FULL_LOAD : PTG_PARTIAL_LOAD);
+    int chain = -1;
+    if (to_partial) chain = src == PTG_DS_OP2_START_F ? PTG_CHAIN_P_FROM_OP2F : src == PTG_DS_OP3_P_F ? PTG_CHAIN_P_FROM_OP3 : -1;
+    else chain = src == PTG_DS_OP1_START_P ? PTG_CHAIN_F_FROM_OP1 : src == PTG_DS_OP8_F_P ? PTG_CHAIN_F_FROM_OP8 : -1;
+    uint32_t c = chain_pack(to_partial ? PTG_DS_OP8_F_P : PTG_DS_OP3_P_F, PTG_CHAIN_J_ONE, 0);   // :684-688, :750-754
+    if (chain >= 0) {
+        int t_op = min(i + j * P.S, P.chain_top);
+        PTG_CHECK_INDEX(P, t_op, P.chain_top + 1, 3);
+        c = __ldg(P.chain_tab + chain * (P.chain_top + 1) + t_op);
+    }
+    return c;
+}
+
 __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, const Plan& p, int& i, int& j,
                                                 uint32_t& meta, int lut_val, const uint64_t* zig_kiwi,
-                                                uint32_t& draws_ep) {
+                                                uint32_t& draws_ep, uint32_t chain_c) {
     const int S = P.S;
     int state = meta & 7, ds = p.ds, next_state, change = 0;
     if (p.kind == PTG_KIND_CONT) {
@@ -513,16 +534,7 @@ __device__ __forceinline__ int apply_transition(const DevParams& P, int64_t e, c
     } else {                                                                     // _partial / _full
         const bool to_partial = p.kind == PTG_KIND_PARTIAL;
         state = next_state = to_partial ? PTG_PARTIAL_LOAD : PTG_FULL_LOAD;
-        const uint32_t src = meta_tab(meta, to_partial ? PTG_FULL_LOAD : PTG_PARTIAL_LOAD);
-        int chain = -1;
-        if (to_partial) chain = src == PTG_DS_OP2_START_F ? PTG_CHAIN_P_FROM_OP2F : src == PTG_DS_OP3_P_F ? PTG_CHAIN_P_FROM_OP3 : -1;
-        else chain = src == PTG_DS_OP1_START_P ? PTG_CHAIN_F_FROM_OP1 : src == PTG_DS_OP8_F_P ? PTG_CHAIN_F_FROM_OP8 : -1;
-        uint32_t c = chain_pack(to_partial ? PTG_DS_OP8_F_P : PTG_DS_OP3_P_F, PTG_CHAIN_J_ONE, 0);   // :684-688, :750-754
-        if (chain >= 0) {
-            int t_op = min(i + j * S, P.chain_top);
-            PTG_CHECK_INDEX(P, t_op, P.chain_top + 1, 3);
-            c = __ldg(P.chain_tab + chain * (P.chain_top + 1) + t_op);
-        }
+        const uint32_t c = PTG_CHAIN_EARLY ? chain_c : chain_lookup(P, p, meta, i, j);
         ds = c >> 27;
         const uint32_t rule = (c >> 25) & 3u;
         const int new_i = (int)(c & 0x1ffffffu);

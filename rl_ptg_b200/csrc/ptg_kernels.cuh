@@ -159,25 +159,41 @@ __global__ void k_build_argmin(const __grid_constant__ BuildParams B, int32_t* l
     }
 }
 
-// hour rows: [pa fp32 window | ... | packed part_full (2 bits each) | el fp64] in nv 16-byte vectors
-__global__ void k_build_hour_tab(const double* e_r_b, int n_hours, int pa, int nv, int raw, double lo, double hi,
+// hour rows: [pa fp32 window | ... | packed part_full (2 bits each) | el fp64] in nv 16-byte vectors.
+// Two layouts of the fp32 slots (the el price always sits in the last 8 bytes):
+//   straight     window value a in slot a, the packed Part_Full codes in slot 4*nv - 3
+//   interleaved  (PTG_HOUR_PAIRED, 64-byte rows of the key-major layout) first 32-byte half = even window values
+//                a = 0, 2, ..., 12 + the packed codes, second half = odd values a = 1, 3, ..., 11 + el: a lane PAIR of the
+//                step kernel gathers its two rows half by half (each LDG.256 touches 16 lines, not 32) and every lane
+//                stages what it loaded -- value a of a row goes to column a of the staged tile, so even / odd lanes
+//                fill even / odd columns without bank conflicts and without exchanging the window values
+#ifndef PTG_HOUR_PAIRED
+#define PTG_HOUR_PAIRED 1
+#endif
+PTG_HD constexpr bool hour_interleaved(int nv, bool flat) { return PTG_HOUR_PAIRED && nv == 4 && !flat; }
+PTG_HD constexpr int hour_slot(int nv, bool flat, int a) {           // fp32 slot of window value a
+    return hour_interleaved(nv, flat) ? ((a & 1) ? 8 + (a >> 1) : (a >> 1)) : a;
+}
+PTG_HD constexpr int hour_bits_slot(int nv, bool flat) { return hour_interleaved(nv, flat) ? 7 : 4 * nv - 3; }
+
+__global__ void k_build_hour_tab(const double* e_r_b, int n_hours, int pa, int nv, int raw, int flat, double lo, double hi,
                                  float* out, uint32_t* err) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_hours) return;
     float* row = out + (int64_t)t * nv * 4;
     const int src = raw ? 0 : 1;       // raw: el price window (:209) | mod: potential reward window (:208)
     uint32_t bits = 0;
+    for (int a = 0; a < nv * 4 - 2; ++a) row[a] = 0.f;
     for (int a = 0; a < pa; ++a) {
         double v = e_r_b[((int64_t)src * pa + a) * n_hours + t];
-        row[a] = (float)((v - lo) / (hi - lo));
+        row[hour_slot(nv, flat != 0, a)] = (float)((v - lo) / (hi - lo));
         double pf = e_r_b[((int64_t)2 * pa + a) * n_hours + t];
         const bool ok = (pf == -1.0) || (pf == 0.0) || (pf == 1.0);
         if (!ok && !raw) atomicOr(err, PTG_EBIT_PARTFULL);
         const int code = ok ? (int)pf : 0;                 // 2-bit two's complement: -1 -> 0b11, 0 -> 0b00, 1 -> 0b01
         bits |= (uint32_t)(code & 3) << (2 * a);
     }
-    for (int a = pa; a < nv * 4 - 3; ++a) row[a] = 0.f;
-    row[nv * 4 - 3] = __uint_as_float(bits);
+    row[hour_bits_slot(nv, flat != 0)] = __uint_as_float(bits);
     *reinterpret_cast<double*>(row + nv * 4 - 2) = e_r_b[t];          // e_r_b[0, 0, t]
 }
 
@@ -262,15 +278,63 @@ __device__ __forceinline__ void stage_windows(const DevParams& P, float* sm, int
     float* rowA = sm + lane * pa;
 #pragma unroll
     for (int a = 0; a < 4 * NV - 3; ++a)
-        if (a < pa) rowA[a] = w[a];
+        if (a < pa) rowA[a] = w[hour_slot(NV, false, a)];
     if (MOD) {
         // Part_Full (:239): 2-bit two's-complement codes (-1, 0, +1) -> sign-extending bit-field extract
-        const int bits = __float_as_int(w[4 * NV - 3]);
+        const int bits = __float_as_int(w[hour_bits_slot(NV, false)]);
         float* rowB = sm + PTG_STAGE_FLOATS(NV) + lane * pa;
 #pragma unroll
         for (int a = 0; a < 16 && a < 4 * NV - 3; ++a)
             if (a < pa) rowB[a] = (float)((bits << (30 - 2 * a)) >> 30);
     }
+}
+
+// Full warps of the key-major layout with 64-byte interleaved hour rows (PTG_HOUR_PAIRED): lanes 2p and 2p + 1 gather
+// their two rows TOGETHER -- the even lane the first 32-byte halves (even window values + Part_Full codes), the odd
+// lane the second halves (odd window values + el price) -- so that each LDG.256 of the warp touches 16 lines instead
+// of 32 (the L1TEX data pipe pays per instruction and 128-byte line: 64 -> 32 wavefronts per warp-step), and each lane
+// stages what it holds: columns of its own parity in both rows of the pair (bank = 26p + 13r + 2c + parity: conflict
+// free).  Exchanged between the lanes: the row index, the two Part_Full words and one el price.  Returns the lane's el.
+template <bool MOD>
+__device__ __forceinline__ double stage_windows_paired(const DevParams& P, float* sm, int lane, int t_hour) {
+    constexpr int pa = 13;
+    if (elect_one()) tma_store_wait_read();       // (as in stage_windows: previous bulk stores are done with sm)
+    __syncwarp();
+    const int t_p = __shfl_xor_sync(0xffffffffu, t_hour, 1);
+    const int odd = lane & 1;
+    const char* base = reinterpret_cast<const char*>(P.hour_tab) + 32 * odd;
+    const U256 h0 = ldg256_nc(base + (int64_t)(odd ? t_p : t_hour) * 64);      // half `odd` of the even lane's row
+    const U256 h1 = ldg256_nc(base + (int64_t)(odd ? t_hour : t_p) * 64);      // half `odd` of the odd lane's row
+    float* rowA = sm + (lane - odd) * pa + odd;                                // row 2p, columns of this lane's parity
+    const unsigned long long q0[4] = {h0.a, h0.b, h0.c, h0.d}, q1[4] = {h1.a, h1.b, h1.c, h1.d};
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {                 // slots 0..5 of the half: a = 2c + odd
+        rowA[2 * c] = __uint_as_float((uint32_t)(q0[c >> 1] >> (32 * (c & 1))));
+        rowA[pa + 2 * c] = __uint_as_float((uint32_t)(q1[c >> 1] >> (32 * (c & 1))));
+    }
+    if (!odd) {                                   // slot 6 of the first half: a = 12 (the second half has el there)
+        rowA[12] = __uint_as_float((uint32_t)h0.d);
+        rowA[pa + 12] = __uint_as_float((uint32_t)h1.d);
+    }
+    if (MOD) {
+        // Part_Full codes of both rows live in slot 7 of the first halves (even lane); the odd lane gets a copy, then
+        // every lane decodes the columns of its parity: a = 2c + odd -> pre-shift by 2 * odd, compile-time shifts after
+        const int b0 = __shfl_sync(0xffffffffu, (int)(h0.d >> 32), lane & ~1) >> (2 * odd);
+        const int b1 = __shfl_sync(0xffffffffu, (int)(h1.d >> 32), lane & ~1) >> (2 * odd);
+        float* rowB = rowA + PTG_STAGE_FLOATS(4);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            rowB[2 * c] = (float)((b0 << (30 - 4 * c)) >> 30);
+            rowB[pa + 2 * c] = (float)((b1 << (30 - 4 * c)) >> 30);
+        }
+        if (!odd) {
+            rowB[12] = (float)((b0 << 6) >> 30);
+            rowB[pa + 12] = (float)((b1 << 6) >> 30);
+        }
+    }
+    // el price (last 8 bytes of the second half): the odd lane holds its own in h1 and its partner's in h0
+    const unsigned long long el_p = __shfl_xor_sync(0xffffffffu, h0.d, 1);
+    return __longlong_as_double((long long)(odd ? h1.d : el_p));
 }
 
 // The warp's two staged window tiles leave the SM as one bulk async copy (TMA) each.
@@ -343,9 +407,9 @@ struct ObsKey {
 template <int NV, bool MOD>
 __device__ __noinline__ void emit_obs_scalar(const DevParams& P, float* __restrict__ obs, int64_t e, ObsKey key) {
     const float* w = reinterpret_cast<const float*>(P.hour_tab + (int64_t)key.t_hour * NV);
-    for (int a = 0; a < P.pa; ++a) obs[P.off_win0 + e * P.pa + a] = w[a];
+    for (int a = 0; a < P.pa; ++a) obs[P.off_win0 + e * P.pa + a] = w[hour_slot(NV, false, a)];
     if (MOD) {
-        const uint32_t bits = __float_as_uint(w[4 * NV - 3]);
+        const uint32_t bits = __float_as_uint(w[hour_bits_slot(NV, false)]);
         for (int a = 0; a < P.pa; ++a) obs[P.off_win1 + e * P.pa + a] = (float)(((int)bits << (30 - 2 * a)) >> 30);
     } else {
         const DayRow day = P.day_tab[key.t_day];
@@ -660,6 +724,9 @@ __device__ __noinline__ void finish_episode(const DevParams& P, const PtgIO& io,
 #ifndef PTG_PERSIST_ALL
 #define PTG_PERSIST_ALL 1        // single steps run persistent CTAs in both layouts (0: key-major with one tile per CTA, round 1)
 #endif
+#ifndef PTG_RNG_PREFETCH
+#define PTG_RNG_PREFETCH 0       // 1: L1 prefetch of a drawing lane's RNG record as soon as (action, state) are known (round 1;
+#endif                           //    it costs the L1TEX data pipe as many wavefronts as the load it hides: 53.2 vs 52.3 us without)
 #ifndef PTG_STEP_MIN_BLOCKS
 #define PTG_STEP_MIN_BLOCKS 4        // CTAs of 256 threads per SM the step kernel is compiled for (<= 64 registers)
 #endif
@@ -764,8 +831,10 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
             PTG_CHECK_INDEX(P, vid, P.n_vals, 4);
             lut_val = ldg32_nc_keep(P.argmin_lut + vid * PTG_N_ARGMIN + plan.col);
         }
+        uint32_t chain_c = 0;
+        if (PTG_CHAIN_EARLY && plan.kind >= PTG_KIND_PARTIAL) chain_c = chain_lookup(P, plan, meta, i, j);
         const bool draws = plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF;
-        if (draws) prefetch_l1(P.rng + e);
+        if (PTG_RNG_PREFETCH && draws) prefetch_l1(P.rng + e);
         // (2) clock of step k+1 (:442-445, integer form of floor(clock_hours), floor(clock_days)) -> market rows of
         //     the NEW hour/day (:446-447) -> observation windows; sin/cos of the clock come from the clock table
         const unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
@@ -775,16 +844,21 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         clamp_market_index(P, t_hour, t_day);
         int k1 = k + 1;
         PTG_CHECK_INDEX(P, k1, P.eps_sim_steps + 1, 5);
-        load_hour_row<NV>(P, t_hour, hrow);
         day = load_day_row(P, t_day);
         const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
-        stage_windows<NV, MOD, PAC>(P, sm, lane, hrow, nvalid == 32);
-        const double el = hour_row_el<NV>(hrow);      // from here on the hour row is dead (registers!)
+        double el;
+        if (hour_interleaved(NV, false) && PAC == 13 && nvalid == 32) {
+            el = stage_windows_paired<MOD>(P, sm, lane, t_hour);
+        } else {
+            load_hour_row<NV>(P, t_hour, hrow);
+            stage_windows<NV, MOD, PAC>(P, sm, lane, hrow, nvalid == 32);
+            el = hour_row_el<NV>(hrow);               // from here on the hour row is dead (registers!)
+        }
         // the window tiles go to the TMA before the transition: the fence in front of a bulk store waits for the
         // thread's outstanding accesses, so it must not sit behind the RNG / step-table requests
         if (!any_done) issue_window_stores<NV, MOD, PAC>(P, obs_out, sm, lane, warp_env0, nvalid);
         // (3) plant transition (requests the RNG record when it draws) -> step-table entry (2 x 32 B sectors)
-        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep);
+        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep, chain_c);
         const int state_change = (prev_state != (int)(meta & 7));
         U256 qc, qn;      // qc = {c_gas, c_eua, c_el, c_0}, qn = {norm[6], tinfo, pad}
         gather_step_entry(P, ent, lane, nvalid, qc, qn);
@@ -880,7 +954,9 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
             PTG_CHECK_INDEX(P, vid, P.n_vals, 4);
             lut_val = ldg32_nc_keep(P.argmin_lut + vid * PTG_N_ARGMIN + plan.col);
         }
-        if (plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF) prefetch_l1(P.rng + e);
+        uint32_t chain_c = 0;
+        if (PTG_CHAIN_EARLY && plan.kind >= PTG_KIND_PARTIAL) chain_c = chain_lookup(P, plan, meta, i, j);
+        if (PTG_RNG_PREFETCH && plan.kind == PTG_KIND_DRAW && P.noise_mode != PTG_NOISE_OFF) prefetch_l1(P.rng + e);
         const unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
         int t_hour = ep.x + (int)(sec / 3600u), t_day = ep.y + (int)(sec / 86400u);
         clamp_market_index(P, t_hour, t_day);
@@ -891,7 +967,7 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
         const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
         stage_flat_early<MOD>(row, hrow, day, pf0, pr12);
         const double el = hour_row_el<4>(hrow);
-        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep);
+        const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep, chain_c);
         const int state_change = (prev_state != (int)(meta & 7));
         U256 qc, qn;
         gather_step_entry(P, ent, lane, nvalid, qc, qn);
