@@ -170,6 +170,9 @@ __global__ void k_build_argmin(const __grid_constant__ BuildParams B, int32_t* l
 #ifndef PTG_HOUR_PAIRED
 #define PTG_HOUR_PAIRED 1
 #endif
+#ifndef PTG_FLAT_PAIRED
+#define PTG_FLAT_PAIRED 1        // flat layout (straight rows): pair gather as well (stage_flat_early_paired)
+#endif
 PTG_HD constexpr bool hour_interleaved(int nv, bool flat) { return PTG_HOUR_PAIRED && nv == 4 && !flat; }
 PTG_HD constexpr int hour_slot(int nv, bool flat, int a) {           // fp32 slot of window value a
     return hour_interleaved(nv, flat) ? ((a & 1) ? 8 + (a >> 1) : (a >> 1)) : a;
@@ -498,6 +501,40 @@ __device__ __forceinline__ void stage_flat_late(float* row, const ObsRegs& o, fl
 __device__ __forceinline__ float4 f4_lo(unsigned long long a, unsigned long long b) {
     return make_float4(__uint_as_float((uint32_t)a), __uint_as_float((uint32_t)(a >> 32)), __uint_as_float((uint32_t)b),
                        __uint_as_float((uint32_t)(b >> 32)));
+}
+
+// Flat layout, mod design, full warps: the 64-byte (straight) hour rows of lanes 2p and 2p + 1 are gathered by the pair
+// -- even lane: Pot_Reward 0..7 of both rows, odd lane: Pot_Reward 8..12, the Part_Full word and the el price of both
+// (each LDG.256 touches 16 lines instead of 32, see stage_windows_paired) -- and each lane stages the Pot_Reward groups
+// it holds for BOTH rows; the Part_Full groups stay with the row's own lane, which gets {Pot_Reward[12], codes} and el
+// from the odd lane with two 64-bit shuffles.  Returns the lane's el price.
+__device__ __forceinline__ double stage_flat_early_paired(const DevParams& P, float* sm, int lane, int t_hour, float& pf0,
+                                                          float& pr12) {
+    const int t_p = __shfl_xor_sync(0xffffffffu, t_hour, 1);
+    const int odd = lane & 1;
+    const char* base = reinterpret_cast<const char*>(P.hour_tab) + 32 * odd;
+    const U256 h0 = ldg256_nc(base + (int64_t)(odd ? t_p : t_hour) * 64);      // half `odd` of the even lane's row
+    const U256 h1 = ldg256_nc(base + (int64_t)(odd ? t_hour : t_p) * 64);      // half `odd` of the odd lane's row
+    float4* r0 = reinterpret_cast<float4*>(sm + (lane - odd) * 40);            // row 2p; row 2p + 1 follows 10 groups later
+    const int g = odd ? 8 : 6;                                                 // Pot_Reward 8..11 | 0..3
+    r0[g] = f4_lo(h0.a, h0.b);
+    r0[10 + g] = f4_lo(h1.a, h1.b);
+    if (!odd) {                                                                // Pot_Reward 4..7
+        r0[7] = f4_lo(h0.c, h0.d);
+        r0[17] = f4_lo(h1.c, h1.d);
+    }
+    const unsigned long long c_p = __shfl_xor_sync(0xffffffffu, h0.c, 1), d_p = __shfl_xor_sync(0xffffffffu, h0.d, 1);
+    const unsigned long long c_own = odd ? h1.c : c_p, d_own = odd ? h1.d : d_p;
+    pr12 = __uint_as_float((uint32_t)c_own);
+    const int bits = (int)(c_own >> 32);
+    auto pf = [bits](int a) { return (float)((bits << (30 - 2 * a)) >> 30); };
+    float4* r4 = reinterpret_cast<float4*>(sm + lane * 40);
+    r4[3] = make_float4(pf(1), pf(2), pf(3), pf(4));
+    r4[4] = make_float4(pf(5), pf(6), pf(7), pf(8));
+    r4[5] = make_float4(pf(9), pf(10), pf(11), pf(12));
+    pf0 = pf(0);
+    __syncwarp();          // (a lane that ends its episode re-stages its own row later: order it behind the partner's stores)
+    return __longlong_as_double((long long)d_own);
 }
 
 template <int NV>
@@ -960,13 +997,18 @@ __device__ __forceinline__ void step_one_flat(const DevParams& P, const PtgIO& i
         const unsigned sec = (unsigned)(k + 1) * (unsigned)P.sim_step;
         int t_hour = ep.x + (int)(sec / 3600u), t_day = ep.y + (int)(sec / 86400u);
         clamp_market_index(P, t_hour, t_day);
-        load_hour_row<4>(P, t_hour, hrow);
         day = load_day_row(P, t_day);
         int k1 = k + 1;
         PTG_CHECK_INDEX(P, k1, P.eps_sim_steps + 1, 5);
         const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
-        stage_flat_early<MOD>(row, hrow, day, pf0, pr12);
-        const double el = hour_row_el<4>(hrow);
+        double el;
+        if (MOD && PTG_FLAT_PAIRED && nvalid == 32) {
+            el = stage_flat_early_paired(P, sm, lane, t_hour, pf0, pr12);
+        } else {
+            load_hour_row<4>(P, t_hour, hrow);
+            stage_flat_early<MOD>(row, hrow, day, pf0, pr12);
+            el = hour_row_el<4>(hrow);
+        }
         const int ent = apply_transition(P, e, plan, i, j, meta, lut_val, zig_kiwi, draws_ep, chain_c);
         const int state_change = (prev_state != (int)(meta & 7));
         U256 qc, qn;
