@@ -282,3 +282,67 @@ def test_benchmarked_workload_matches_oracle(layout):
     for f in ("meth_state", "i", "j", "k", "hot_cold", "partial_ds", "full_ds", "act_ep_h", "act_ep_d", "episode_count", "draws"):
         assert np.array_equal(so[f], sg[f]), f
     env.close(); ora.close()
+
+
+@pytest.mark.parametrize("layout", ["dict", "flat"])
+def test_sticky_policy_matches_oracle(layout):
+    """A policy that holds its action for tens of steps (what a trained agent does): most warps consist of envs that ALL
+    continue their current table, which the step kernels serve on a fast path (step-table entry requested before the
+    transition, cont_entry / cont_advance).  8 192 envs x 260 steps against the CPU oracle with full observations:
+    tables run to their ends (start-up hands over to partial load, the last row repeats), the load-change chains see
+    long dwell times, one episode end (201 steps) with its auto-reset; single steps and the roll-out kernel."""
+    import torch
+    from oracle.ptg_oracle import OracleVecEnv, draw_noise_tape
+    kw = dict(synthetic_kwargs(dict(scenario=2, operation="OP2")))
+    kw["eps_sim_steps"] = 206                     # episodes of 201 steps
+    n, steps, pa = 8192, 260, int(kw["price_ahead"])
+    seeds = 3654 + np.arange(n)
+    rng = np.random.default_rng(7)
+    # actions: every BLOCK of 64 envs (two warps) switches at its own random times, envs inside a block mostly agree on
+    # when to hold (so that whole warps continue) but not on what: a new action per env at a switch
+    acts = np.empty((steps, n), dtype=np.int64)
+    cur = rng.integers(0, 5, size=n)
+    next_switch = rng.integers(1, 60, size=n // 64)
+    for t in range(steps):
+        sw = np.repeat(next_switch == t, 64)
+        lone = rng.random(n) < 0.002              # a few envs switch on their own (mixed warps)
+        new = rng.integers(0, 5, size=n)
+        cur = np.where(sw | lone, new, cur)
+        next_switch = np.where(next_switch == t, t + rng.integers(5, 90, size=n // 64), next_switch)
+        acts[t] = cur
+    ora = OracleVecEnv(kw, n, noise_tape=draw_noise_tape(seeds, kw["noise"], steps), threads=len(os.sched_getaffinity(0)))
+    env = make_env(kw, n, seed=3654, obs_layout=layout)
+    twin = make_env(kw, n, seed=3654, obs_layout=layout)       # the same actions through the roll-out kernel
+    ora.reset()
+    if layout == "dict":
+        obs = env.reset(); keys = list(obs.keys())
+    else:
+        env.reset_tensor()
+    twin.reset_tensor()
+    T = 20
+    n_done = 0
+    for t in range(steps):
+        o_obs, o_rew, o_done = ora.step(acts[t])
+        if layout == "dict":
+            obs, rew, done, infos = env.step(acts[t])
+            got, want = flat_obs(obs, keys), o_obs
+        else:
+            _, rew_t, done_t = env.step_tensor(torch.as_tensor(acts[t], device=env.device))
+            rew, done = rew_t.cpu().numpy(), done_t.cpu().numpy().astype(bool)
+            got, want = env.features_view().cpu().numpy(), _oracle_features(o_obs, pa)
+        assert np.array_equal(done, o_done.astype(bool)), f"done step {t}"
+        assert_close_fp32(rew, o_rew, f"reward step {t}")
+        assert_close_fp32(got, want, f"obs step {t}")
+        n_done += int(o_done.sum())
+        if t % T == 0:                                         # roll-out twin: T steps in one launch
+            out = twin.rollout_tensor(torch.as_tensor(acts[t:t + T], device=twin.device))
+            roll_rew, roll_done = out["reward"].cpu().numpy(), out["done"].cpu().numpy().astype(bool)
+        assert np.array_equal(roll_done[t % T], o_done.astype(bool)), f"roll-out done step {t}"
+        assert_close_fp32(roll_rew[t % T], o_rew, f"roll-out reward step {t}")
+    assert n_done == n
+    so = ora.get_state()
+    for e_ in (env, twin):
+        sg = e_.get_state()
+        for f in ("meth_state", "i", "j", "k", "hot_cold", "partial_ds", "full_ds", "act_ep_h", "act_ep_d", "episode_count", "draws"):
+            assert np.array_equal(so[f], sg[f]), f
+    env.close(); twin.close(); ora.close()
