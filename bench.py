@@ -461,8 +461,8 @@ def run_gpu(args):
         _lib.check(_lib.load().ptg_probe_box(local_rank, ctypes.byref(out4)))
         box_probe = {"l2_dependent_load_ns": round(out4[0], 1), "dram_dependent_load_ns": round(out4[1], 1),
                      "sm_clock_mhz_seen_by_a_thread": round(out4[2], 1),
-                     "note": "the step kernel is bound by latency x occupancy, not by HBM bandwidth: boxes of this pool "
-                             "with the same copy bandwidth run the same binary 58 or 66 us per step (DESIGN.md section 7)"}
+                     "note": "the step kernel is bound by L1TEX wavefronts and latency, not by HBM bandwidth: boxes of this "
+                             "pool with the same copy bandwidth run the same binary up to 14 % apart (DESIGN.md section 7)"}
 
     # ---------------- rollout kernel (T steps per launch), reported in config ----------------
     T = 16
