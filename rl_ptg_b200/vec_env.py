@@ -197,6 +197,9 @@ class PtGVecEnv(_Base):
         self._win_flag = torch.zeros(1, dtype=torch.int32, device=dev)     # PtgIO.windows_changed (step serial stamp)
         self._status_d = torch.zeros(n, dtype=torch.uint8, device=dev)     # PtgIO.status_u8: METH_STATUS, one byte per env
         self._status_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        # METH_STATUS as the Discrete(6) space's int64, handed out as a view of one of two reused buffers (valid until
+        # the step after next, like every other observation block); filled by torch's multi-threaded converting copy
+        self._status_i64 = [torch.zeros(n, dtype=torch.int64) for _ in range(2)]
         self._clock_ok = True                    # the library's shared-clock tracking saw every step (no graph replays)
         self._obs_dict = self._obs_views(self._obs)          # views are created once; buffers are reused
         self._io = self._make_io(self._obs, self._reward, self._done, self._term_obs,
@@ -409,7 +412,9 @@ class PtGVecEnv(_Base):
         rewards = reward_h.numpy()
         any_done = bool(dones.any())
         self._ev_scalars.synchronize()
-        status = self._status_h.numpy().astype(np.int64)
+        status_t = self._status_i64[self._flip]
+        status_t.copy_(self._status_h)                 # uint8 -> int64 (0.09 ms at 1 M envs; numpy's astype: 0.6 ms)
+        status = status_t.numpy()
         if any_done:
             self._term_obs_h.copy_(self._term_obs, non_blocking=True)
             self._ep_ret_h.copy_(self._ep_ret, non_blocking=True)
