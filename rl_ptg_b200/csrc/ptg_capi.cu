@@ -355,6 +355,15 @@ extern "C" int ptg_create(const PtgConfig* cfg, const PtgTables* tables, int64_t
     PTG_TRY(h->alloc(&day_tab, (size_t)tables->n_days));
     k_build_day_tab<<<blocks_for(tables->n_days, 128), 128>>>(d_ge, P.n_days, c.gas_l_b, c.gas_u_b, c.eua_l_b, c.eua_u_b, day_tab);
     P.day_tab = day_tab;
+    P.hourq_tab = nullptr;
+    if (PTG_HOUR_QUAD && !P.raw && !P.flat && P.pa == 13 && !getenv("PTG_NO_HOUR_QUAD")) {   // (the switch: kernel A/Bs only)
+        float* hourq_tab = nullptr;
+        PTG_TRY(h->alloc(&hourq_tab, (size_t)tables->n_hours * 32));
+        k_build_hourq_tab<<<blocks_for(tables->n_hours, 128), 128>>>(d_erb, d_ge, P.n_hours, P.n_days, c.rew_l_b, c.rew_u_b,
+                                                                    hourq_tab);
+        P.hourq_tab = hourq_tab;
+        h->launches += 1;
+    }
     ClockRow* clock_tab = nullptr;
     PTG_TRY(h->alloc(&clock_tab, (size_t)c.eps_sim_steps + 1));
     k_build_clock_tab<<<blocks_for(c.eps_sim_steps + 1, 128), 128>>>(c.eps_sim_steps + 1, c.sim_step, clock_tab);

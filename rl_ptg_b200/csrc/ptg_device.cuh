@@ -245,6 +245,7 @@ struct DevParams {
     const int32_t* argmin_lut;     // [n_vals][6]
     const float4* hour_tab;        // [n_hours][nv]
     const DayRow* day_tab;         // [n_days]
+    const float* hourq_tab;        // [n_hours][32] quad hour rows incl. the day's prices (k_build_hourq_tab) or nullptr
     const ClockRow* clock_tab;     // [eps_sim_steps + 1]
     const int64_t* eps_ind;        // [n_eps_ind] or nullptr
     const uint16_t* plan_lut;      // [PTG_PLAN_LUT_SIZE] plan_pack() of every (action, state, T flags, hot_cold)

@@ -170,6 +170,10 @@ __global__ void k_build_argmin(const __grid_constant__ BuildParams B, int32_t* l
 #ifndef PTG_HOUR_PAIRED
 #define PTG_HOUR_PAIRED 1
 #endif
+#ifndef PTG_HOUR_QUAD
+#define PTG_HOUR_QUAD 0          // 1: key-major mod layout, price_ahead 13: 128-byte hour rows with the day's prices, gathered by
+#endif                           //    lane quads (no day-row gather).  Parity-green, but no faster: 52.7 vs 52.7 us uniform, 42.2 vs
+                                 //    42.3 us sticky, and the roll-out kernel spills (32.9 vs 29.9 us) -- DESIGN.md section 7
 #ifndef PTG_FLAT_PAIRED
 #define PTG_FLAT_PAIRED 1        // flat layout (straight rows): pair gather as well (stage_flat_early_paired)
 #endif
@@ -212,6 +216,36 @@ __global__ void k_build_day_tab(const double* g_e, int n_days, double gas_lo, do
     r.eua_n0 = (float)((g_e[(int64_t)2 * n_days + d] - eua_lo) / (eua_hi - eua_lo));        // :211
     r.eua_n1 = (float)((g_e[(int64_t)3 * n_days + d] - eua_lo) / (eua_hi - eua_lo));
     out[d] = r;
+}
+
+// Quad hour rows (PTG_HOUR_QUAD; mod design, price_ahead == 13, key-major layout): ONE 128-byte line per hour that also
+// carries the day's {gas, eua} -- for an env whose episode starts on a day boundary (act_ep_h == 24 * act_ep_d, true for
+// every integer eps_len_d) the day index is t_hour / 24, so the day-row gather (32 more lines per warp-step on the
+// L1TEX data pipe) disappears.  The row is four 32-byte quarters, one per lane of a lane QUAD (stage_windows_quad):
+//   quarter q:  fp32 slots 0..3 = window values a = q, q + 4, q + 8, q + 12 (a < 13) | slot 4 = the packed Part_Full
+//               codes of all 13 values (a copy per quarter) | slot 5 = 0 | fp64 in slots 6-7: q0 el, q1 gas, q2 eua, q3 0
+__global__ void k_build_hourq_tab(const double* e_r_b, const double* g_e, int n_hours, int n_days, double lo, double hi,
+                                  float* out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_hours) return;
+    constexpr int pa = 13;
+    float* row = out + (int64_t)t * 32;
+    uint32_t bits = 0;
+    for (int s = 0; s < 32; ++s) row[s] = 0.f;
+    for (int a = 0; a < pa; ++a) {
+        double v = e_r_b[((int64_t)1 * pa + a) * n_hours + t];                  // potential reward window (:208)
+        row[8 * (a & 3) + (a >> 2)] = (float)((v - lo) / (hi - lo));
+        double pf = e_r_b[((int64_t)2 * pa + a) * n_hours + t];
+        const bool ok = (pf == -1.0) || (pf == 0.0) || (pf == 1.0);            // (k_build_hour_tab reports violations)
+        bits |= (uint32_t)((ok ? (int)pf : 0) & 3) << (2 * a);
+    }
+    const int d = min(t / 24, n_days - 1);
+    double* row_d = reinterpret_cast<double*>(row);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) row[8 * q + 4] = __uint_as_float(bits);
+    row_d[3] = e_r_b[t];                          // e_r_b[0, 0, t]
+    row_d[7] = g_e[d];                            // g_e[0, 0, d]
+    row_d[11] = g_e[(int64_t)2 * n_days + d];     // g_e[1, 0, d]
 }
 
 __global__ void k_build_clock_tab(int n, int sim_step, ClockRow* out) {
@@ -338,6 +372,59 @@ __device__ __forceinline__ double stage_windows_paired(const DevParams& P, float
     // el price (last 8 bytes of the second half): the odd lane holds its own in h1 and its partner's in h0
     const unsigned long long el_p = __shfl_xor_sync(0xffffffffu, h0.d, 1);
     return __longlong_as_double((long long)(odd ? h1.d : el_p));
+}
+
+// Full warps whose lanes all sit on a day-aligned clock (t_day == t_hour / 24): the 128-byte quad rows of
+// k_build_hourq_tab.  Lanes 4p .. 4p + 3 gather their four rows TOGETHER -- lane q the q-th 32-byte quarter of each --
+// so every LDG.256 of the warp touches 8 lines and the four of them 32: what the 64-byte rows cost, with the day's gas
+// and EUA price on board (no day-row gather: 64 -> 32 lines per warp-step for the market data).  Each lane stages the
+// columns a = q (mod 4) of the four rows (bank = 20p + 13r + 4c + q: conflict free) and decodes the Part_Full codes of
+// the same columns from its quarter's copy of the code word.  The three prices of a row arrive in three different
+// lanes; they change hands through 768 bytes of the warp's (not yet staged) Part_Full tile.  Returns the lane's el.
+__device__ __forceinline__ double stage_windows_quad(const DevParams& P, float* sm, int lane, int t_hour, double& gas,
+                                                     double& eua) {
+    constexpr int pa = 13;
+    if (elect_one()) tma_store_wait_read();       // (as in stage_windows: previous bulk stores are done with sm)
+    __syncwarp();
+    const int q = lane & 3, l0 = lane & ~3;
+    const char* base = reinterpret_cast<const char*>(P.hourq_tab) + 32 * q;
+    U256 h[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int t_r = __shfl_sync(0xffffffffu, t_hour, l0 + r);
+        h[r] = ldg256_nc(base + (int64_t)t_r * 128);                            // quarter q of the row of lane 4p + r
+    }
+    double* xb = reinterpret_cast<double*>(sm + PTG_STAGE_FLOATS(4));           // [32 rows][el, gas, eua]
+    if (q < 3) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) xb[(l0 + r) * 3 + q] = __longlong_as_double((long long)h[r].d);
+    }
+    float* rowA = sm + l0 * pa + q;                                             // row 4p, column q
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        rowA[r * pa] = __uint_as_float((uint32_t)h[r].a);
+        rowA[r * pa + 4] = __uint_as_float((uint32_t)(h[r].a >> 32));
+        rowA[r * pa + 8] = __uint_as_float((uint32_t)h[r].b);
+    }
+    if (q == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rowA[r * pa + 12] = __uint_as_float((uint32_t)(h[r].b >> 32));
+    }
+    __syncwarp();
+    const double el = xb[lane * 3];
+    gas = xb[lane * 3 + 1];
+    eua = xb[lane * 3 + 2];
+    __syncwarp();                                 // the prices are out: the Part_Full tile may be staged over them
+    float* rowB = rowA + PTG_STAGE_FLOATS(4);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                 // codes of a = 4c + q: pre-shift by 2q, compile-time shifts after
+        const int b = (int)(uint32_t)h[r].c >> (2 * q);
+        rowB[r * pa] = (float)((b << 30) >> 30);
+        rowB[r * pa + 4] = (float)((b << 22) >> 30);
+        rowB[r * pa + 8] = (float)((b << 14) >> 30);
+        if (q == 0) rowB[r * pa + 12] = (float)((b << 6) >> 30);
+    }
+    return el;
 }
 
 // The warp's two staged window tiles leave the SM as one bulk async copy (TMA) each.
@@ -847,7 +934,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
                                          float* __restrict__ rew_out, uint8_t* __restrict__ done_out, int& i, int& j,
                                          int& k, uint32_t& meta, int32_t& tinfo, int2& ep, double& ep_ret) {
     float4 hrow[NV];
-    DayRow day;
+    DayRow day = {};
     ObsRegs o;
     float reward = 0.f;
     int t_hour_out = 0;
@@ -881,10 +968,15 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         clamp_market_index(P, t_hour, t_day);
         int k1 = k + 1;
         PTG_CHECK_INDEX(P, k1, P.eps_sim_steps + 1, 5);
-        day = load_day_row(P, t_day);
+        // quad rows carry the day's prices: usable by a full warp whose lanes all have t_day == t_hour / 24
+        const bool quad = PTG_HOUR_QUAD && MOD && NV == 4 && PAC == 13 && nvalid == 32 && P.hourq_tab != nullptr &&
+                          __all_sync(0xffffffffu, (unsigned)(t_hour - 24 * t_day) < 24u);
+        if (!quad) day = load_day_row(P, t_day);
         const float2 sc2 = __ldg(reinterpret_cast<const float2*>(P.clock_tab + k1));
-        double el;
-        if (hour_interleaved(NV, false) && PAC == 13 && nvalid == 32) {
+        double el, gas = day.gas, eua = day.eua;
+        if (quad) {
+            el = stage_windows_quad(P, sm, lane, t_hour, gas, eua);
+        } else if (hour_interleaved(NV, false) && PAC == 13 && nvalid == 32) {
             el = stage_windows_paired<MOD>(P, sm, lane, t_hour);
         } else {
             load_hour_row<NV>(P, t_hour, hrow);
@@ -902,7 +994,7 @@ __device__ __forceinline__ void step_one(const DevParams& P, const PtgIO& io, lo
         // reward (:280-334 in price-linear form) with the prices of the new hour/day (:463-468)
         const double c_gas = __longlong_as_double((long long)qc.a), c_eua = __longlong_as_double((long long)qc.b);
         const double c_el = __longlong_as_double((long long)qc.c), c_0 = __longlong_as_double((long long)qc.d);
-        double rew = __fma_rn(c_gas, day.gas, __fma_rn(c_eua, day.eua, __fma_rn(-c_el, el, c_0)));
+        double rew = __fma_rn(c_gas, gas, __fma_rn(c_eua, eua, __fma_rn(-c_el, el, c_0)));
         if (state_change) rew -= P.penalty;
         ep_ret += rew;
         reward = (float)rew;

@@ -586,3 +586,39 @@ def test_numpy_api_clock_blocks_with_and_without_a_shared_clock():
     assert obs["Temp_hour_enc_sin"].strides == (0, 0)
     check(obs, "after the full reset")
     env.close()
+
+
+def test_episodes_that_start_off_a_day_boundary():
+    """eps_len_d = 18.5: every other episode starts at noon (act_ep_h == 24 * act_ep_d + 12), so from the 13th hour of
+    the episode on its day index is NOT t_hour // 24.  Full warps take the quad hour rows (which carry the prices of day
+    t_hour // 24) while all their lanes are day-aligned and the pair rows + day-row gather afterwards: both paths, the
+    switch between them, single steps and the roll-out kernel against the oracle."""
+    kw = synthetic_kwargs(dict(scenario=2, operation="OP2", eps_len_d=18.5))
+    n, steps, T = 1024 + 37, 160, 16
+    seeds = 3654 + np.arange(n)
+    ora = _oracle(kw, n, steps, seeds)
+    env = make_env(kw, n, seed=3654)
+    env2 = make_env(kw, n, seed=3654)
+    ora.reset(); obs = env.reset(); env2.reset()
+    st = env.get_state()
+    off = st["act_ep_h"] - 24 * st["act_ep_d"]
+    assert set(np.unique(off)) == {0, 12}
+    keys = list(obs.keys())
+    rng = np.random.default_rng(5)
+    acts = rng.integers(0, 5, size=(steps, n))
+    import torch
+    for t0 in range(0, steps, T):
+        roll = env2.rollout_tensor(torch.as_tensor(acts[t0:t0 + T], device=env2.device))
+        r_rew = roll["reward"].cpu().numpy()
+        for t in range(t0, t0 + T):
+            o_obs, o_rew, o_done = ora.step(acts[t])
+            obs, rew, done, _ = env.step(acts[t])
+            assert np.array_equal(done, o_done.astype(bool))
+            assert_close_fp32(rew, o_rew, f"reward step {t}")
+            assert_close_fp32(flat_obs(obs, keys), o_obs, f"obs step {t}")
+            assert np.array_equal(r_rew[t - t0], rew), f"roll-out kernel reward step {t}"
+            r_obs = {k: v.cpu().numpy() for k, v in env2.obs_views_of(roll["obs"][t - t0]).items()}
+            assert np.array_equal(flat_obs(r_obs, keys), flat_obs(obs, keys)), f"roll-out kernel obs step {t}"
+    _assert_state_equal(ora, env, "end")
+    _assert_state_equal(ora, env2, "end (roll-out kernel)")
+    env.close(); env2.close(); ora.close()
