@@ -56,7 +56,125 @@ CASES = {
                          dict(n_envs=2, steps=1200, actions="uniform", split="val", mode="eval", seed=605)),
     "bs3_op2_raw_continuous_penalty": (dict(scenario=3, operation="OP2", raw_modified="raw", state_change_penalty=0.25),
                                        dict(n_envs=2, steps=1500, actions="continuous", action_type="continuous")),
+    # scripted tours through the quirks of SURVEY.md A.9 (closed loop on the reference env, recorded as a tape;
+    # tests/test_quirks.py asserts what each marked step must show).  quirks_s50 moves time2_p_f_p onto a time_op the
+    # 50-row steps can reach (150), so that the strict `<` chains are met with equality.
+    "quirks_s300": (dict(scenario=2, operation="OP2"), dict(n_envs=3, steps=420, actions="tour_s300")),
+    "quirks_s50": (dict(scenario=2, operation="OP2", sim_step=100, time2_p_f_p=150),
+                   dict(n_envs=3, steps=420, actions="tour_s50")),
 }
+
+
+# ---- closed-loop scripts (policy(env, mem) -> action); `mem["marks"]` collects (label, step) pairs -------------
+def _phase(mem):
+    mem.setdefault("ph", 0); mem.setdefault("n", 0); mem.setdefault("marks", []); mem.setdefault("tries", 0)
+    mem["n"] += 1
+    return mem["ph"], mem["n"]
+
+
+def _go(mem, ph):
+    mem["ph"], mem["n"] = ph, 0
+
+
+def tour_s300(env, mem, t):
+    """Default thresholds, S = 300: first step after reset, cold start-up with hand-over, the op1 -> op3 -> op7 chain,
+    an exhausted table, hot/cold hysteresis, both standby tables, index clamp at 0."""
+    ph, n = _phase(mem)
+    st, mark = env.Meth_State, lambda label: mem["marks"].append((label, t))
+    if ph == 0:                      # cont(cooldown) right after reset: j 0 -> 1; on until T_cat <= 15.0 degC
+        if n == 1: mark("first_cont_cooldown")
+        if env.Meth_T_cat <= 15.0: _go(mem, 1)
+        return 1
+    if ph == 1:                      # _standby below the first row of standby_up (15.2): argmin = 0, clamped if noise < 0
+        mark("standby_from_cold"); _go(mem, 2); return 0
+    if ph == 2:                      # cold start-up until the hand-over to partial load
+        if n == 1: mark("startup_cold")
+        if st == 3: mark("handover_done"); _go(mem, 3); return 3
+        return 2
+    if ph == 3:                      # dwell in op1_start_p beyond time1_start_p_f = 1201 rows
+        if env.i + env.j * env.step_size >= 1201 + 300: mark("full_from_op1_late"); _go(mem, 4); return 4
+        return 3
+    if ph == 4:                      # one more full-load step: time_op = 600
+        _go(mem, 5); return 4
+    if ph == 5:                      # time45_p_f_p < 600 < time5_p_f_p: op7_p_f_p_22, i = time5_p_f_p
+        mark("partial_563_675"); _go(mem, 6); return 3
+    if ph == 6:                      # exhaust op7_p_f_p_22 (3 481 rows): padded, then constant last row
+        if n >= 14: mark("full_from_catch_all"); _go(mem, 7); return 4
+        return 3
+    if ph == 7:                      # full load (T_cat >= 350: hot), then standby_down
+        if n >= 3: mark("standby_from_hot"); _go(mem, 8); return 0
+        return 4
+    if ph == 8:                      # standby_down until 160 < T_cat < 350, then a start-up: hot_cold kept at 1
+        if env.Meth_T_cat < 300: mark("startup_in_hysteresis_band"); _go(mem, 9); return 2
+        return 0
+    if ph == 9:
+        if st == 3: mark("cooldown_from_load"); _go(mem, 10); return 1
+        return 2
+    if ph == 10:                     # cooldown below 160 degC: hot_cold -> 0
+        if env.Meth_T_cat < 150: mark("standby_below_188"); _go(mem, 11); return 0
+        return 1
+    if ph == 11:                     # standby_up for a few steps, then a COLD start-up although T_cat > 160
+        if n >= 3: mark("startup_cold_again"); _go(mem, 12); return 2
+        return 0
+    if ph == 12:
+        if st == 3: _go(mem, 13); return 4
+        return 2
+    return 4 if (n // 7) % 2 == 0 else 3
+
+
+def tour_s50(env, mem, t):
+    """S = 50 (sim_step = 100), time2_p_f_p = 150: "fully developed" indices, `j += 1` with i kept, a threshold met with
+    equality, a hot start-up whose noisy index lands past the end of the table."""
+    ph, n = _phase(mem)
+    st, mark = env.Meth_State, lambda label: mem["marks"].append((label, t))
+    t_op = env.i + env.j * env.step_size
+    if ph == 0 and "cold" not in mem:                # start with the cold probes below
+        mem["cold"] = 0; _go(mem, 20); ph = 20
+    if ph == 20:                     # cooldown (cont, or _cooldown after a probe) until T_cat <= 15.2 = standby_up[0:5, T]
+        if env.Meth_T_cat <= 15.2 and st == 1: _go(mem, 21); mark("standby_from_cold"); mem["cold"] += 1; return 0
+        return 1
+    if ph == 21:                     # argmin + noise < 0 -> i = int(max(.., 0)) = 0; repeat until one probe was clamped
+        if env.i == 0 and env.j == 1: mem["marks"].append(("standby_clamped_at_0", t - 1))
+        _go(mem, 0 if ((env.i == 0 and env.j == 1) or mem["cold"] >= 6) else 20)
+        return 1 if mem["ph"] == 20 else 2
+    if ph == 0:                      # cold start-up; right at the hand-over: _full at time_op < time1_start_p_f
+        if st == 3: mark("full_from_op1_early"); _go(mem, 30); return 4
+        return 2
+    if ph == 30:                     # op2_start_f at time_op = 50 < time2_start_f_p: _partial takes i from the argmin
+        mark("partial_argmin_no_noise"); _go(mem, 1); return 3        # of op1_start_p WITHOUT a noise draw (:641)
+    if ph == 1:                      # dwell in op1_start_p beyond time1_start_p_f, then _full -> op3_p_f (0, 1)
+        if t_op >= 1201: mark("full_from_op1_late"); _go(mem, 2); return 4
+        return 3
+    if ph == 2:                      # time_op = 50 < time1_p_f_p = 51
+        mark("partial_fully_developed"); _go(mem, 3); return 3
+    if ph == 3:                      # two steps on the last row of op8_f_p, then _full at time_op = 17 000+
+        if n >= 2: mark("full_from_op8_late"); _go(mem, 4); return 4
+        return 3
+    if ph == 4:                      # cont(full): time_op = 100
+        _go(mem, 5); return 4
+    if ph == 5:                      # 51 < 100 < 150: op4_p_f_p_5, j += 1, i from the previous table
+        mark("partial_keep_i"); _go(mem, 6); return 3
+    if ph == 6:                      # part_op = op4_p_f_p_5: catch-all branch of _full
+        mark("full_from_catch_all"); _go(mem, 7); return 4
+    if ph == 7:
+        if t_op >= 150: mark("partial_at_threshold"); _go(mem, 8); return 3     # time_op == time2_p_f_p
+        return 4
+    if ph == 8:                      # _full from op8_f_p at time_op = 50 < time1_f_p_f = 51
+        mark("full_fully_developed"); _go(mem, 9); return 4
+    if ph == 9:                      # re-heat at full load, one standby step, then a start-up at T_cat > 400 degC:
+        if n >= 6: _go(mem, 10); return 0            # argmin = last row of startup_hot (2 047 of 2 048)
+        return 4
+    if ph == 10:
+        mark("startup_hot_probe"); mem["tries"] += 1; _go(mem, 11); return 2
+    if ph == 11:                     # repeat the probe until the noisy index fell past the end (i >= L; i, j kept)
+        hit = env.j == 1 and env.i >= len(env.startup_hot)
+        if hit: mem["marks"].append(("startup_hot_past_end", t - 1))
+        _go(mem, 12 if (hit or mem["tries"] >= 12) else 9)
+        return 4
+    return 4 if (n // 3) % 2 == 0 else 3
+
+
+SCRIPTS = {"tour_s300": tour_s300, "tour_s50": tour_s50}
 
 
 def make_actions(kind: str, steps: int, n_envs: int, seed: int = 0) -> np.ndarray:
@@ -101,7 +219,9 @@ def run_case(name: str, overrides: dict, opt: dict) -> dict:
     action_type = opt.get("action_type", "discrete")
     sess = ReferenceSession(overrides, action_type=action_type)
     kw = sess.kwargs(split)
-    actions = make_actions(opt["actions"], steps, n_envs)
+    script = SCRIPTS.get(opt["actions"])
+    actions = np.zeros((steps, n_envs), dtype=np.int64) if script else make_actions(opt["actions"], steps, n_envs)
+    mems = [dict() for _ in range(n_envs)]
 
     sess.pg.ep_index = 0                                   # fresh process
     envs = [sess.pg.PTGEnv(kw, mode) for _ in range(n_envs)]          # make_vec_env: constructors in order
@@ -122,6 +242,8 @@ def run_case(name: str, overrides: dict, opt: dict) -> dict:
     running = np.zeros(n_envs)
     for t in range(steps):
         for e, env in enumerate(envs):
+            if script:
+                actions[t, e] = script(env, mems[e], t)
             a = actions[t, e]
             o, r, term, trunc, inf = env.step(np.array([a], dtype=np.float32) if action_type == "continuous" else int(a))
             running[e] += r
@@ -147,7 +269,7 @@ def run_case(name: str, overrides: dict, opt: dict) -> dict:
     out = dict(
         meta=json.dumps(dict(case=name, overrides=overrides, n_envs=n_envs, steps=steps, split=split, mode=mode,
                              seed=seed, action_type=action_type, obs_keys=keys, numpy=np.__version__,
-                             seed_train=3654, seed_test=605)),
+                             seed_train=3654, seed_test=605, marks=[m.get("marks", []) for m in mems])),
         actions=actions, ints=ints, rewards=rewards, obs_steps=keep.astype(np.int32),
         obs=obs_all[keep], reset_obs=np.stack(reset_obs), reset_info=np.stack(reset_info),
         term_steps=np.array(term_steps, dtype=np.int32).reshape(-1, 2),
