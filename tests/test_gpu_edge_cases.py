@@ -590,9 +590,11 @@ def test_numpy_api_clock_blocks_with_and_without_a_shared_clock():
 
 def test_episodes_that_start_off_a_day_boundary():
     """eps_len_d = 18.5: every other episode starts at noon (act_ep_h == 24 * act_ep_d + 12), so from the 13th hour of
-    the episode on its day index is NOT t_hour // 24.  Full warps take the quad hour rows (which carry the prices of day
-    t_hour // 24) while all their lanes are day-aligned and the pair rows + day-row gather afterwards: both paths, the
-    switch between them, single steps and the roll-out kernel against the oracle."""
+    the episode on its day index is NOT t_hour // 24: hour and day rows must be looked up independently.  (In a
+    -DPTG_HOUR_QUAD=1 build full warps take the quad hour rows -- which carry the prices of day t_hour // 24 -- while
+    all their lanes are day-aligned and the pair rows + day-row gather afterwards; this test then covers both paths and
+    the switch between them.  It passed against that build and against the shipped one.)  Single steps and the
+    roll-out kernel against the oracle."""
     kw = synthetic_kwargs(dict(scenario=2, operation="OP2", eps_len_d=18.5))
     n, steps, T = 1024 + 37, 160, 16
     seeds = 3654 + np.arange(n)
