@@ -35,7 +35,8 @@ def draw_trial(rng: np.random.Generator):
     ov = dict(scenario=int(rng.integers(1, 4)), operation=str(rng.choice(["OP1", "OP2"])),
               raw_modified=str(rng.choice(["raw", "mod"])), sim_step=int(rng.choice([100, 120, 200, 300, 600, 900])),
               price_ahead=int(rng.choice([1, 4, 6, 13, 16])), noise=int(rng.choice([0, 3, 10, 40])),
-              state_change_penalty=float(rng.choice([0.0, 0.0, 0.25, 1.5])))
+              state_change_penalty=float(rng.choice([0.0, 0.0, 0.25, 1.5])),
+              eps_len_d=int(rng.choice([1, 37, 37, 41])))       # 1-day episodes: several auto-resets per trial (ep_index)
     base = real_kwargs(dict(scenario=1, operation="OP2"))
     for name in rng.choice(THRESHOLDS, size=int(rng.integers(0, 5)), replace=False):     # move a few thresholds
         S = ov["sim_step"] // 2
